@@ -1,0 +1,184 @@
+/*
+ * tsar_b200.h -- C ABI of the B200-native TSAR-MVS depthmap path.
+ *
+ * This is the drop-in boundary for the per-reference-view depthmap hot path of TSAR-MVS
+ * (reference: gipuma.cu + gSLICr_Lib).  Every entry point names the reference interface it
+ * replaces (file:line relative to the reference checkout).  Plain pointers and sizes only:
+ * no C++ types, no torch types, no managed memory.  All functions return TSAR_OK (0) or a
+ * negative tsar_status; they never call exit() (the reference's checkCudaErrors does,
+ * helper_cuda.h:891-905).  tsar_last_error() gives the text for the last failure on a context.
+ *
+ * Threading: one context = one reference view in flight on one device/stream.  Contexts are
+ * independent; use one per GPU (or several per GPU on different streams) to shard reference
+ * views (reference: one process per view, scripts/pipes.sh:30-49).
+ *
+ * The C++ shims with the reference's own signatures (firstcuda/sliccuda/fakecuda/fillcuda,
+ * gipuma.h:2-5) live in tsar_gipuma_abi.h and are implemented on top of this file.
+ */
+#ifndef TSAR_B200_H
+#define TSAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSAR_MAX_VIEWS 32 /* pmCostMultiview_cu costVector[32], gipuma.cu:467-468 (Q8) */
+
+typedef enum tsar_status {
+    TSAR_OK = 0,
+    TSAR_ERR_ARG = -1,     /* bad argument (null, size, V outside [1,32], ...) */
+    TSAR_ERR_STATE = -2,   /* call order (e.g. iterate before set_views)        */
+    TSAR_ERR_CUDA = -3,    /* a CUDA runtime call failed                        */
+    TSAR_ERR_NOMEM = -4,
+    TSAR_ERR_NODEVICE = -5 /* no CUDA device / not an sm_100 part: there is no CPU fallback */
+} tsar_status;
+
+/* Value fields of Camera_cu (camera.h:7-65) for one view, already moved into the frame of the
+ * reference camera as getCameraParameters(transformP=true) does (cameraGeometryUtils.h:174-364).
+ * All 3x3 matrices row-major. */
+typedef struct tsar_camera {
+    float K[9];          /* camera.h:26  own intrinsics                                   */
+    float K_inv[9];      /* camera.h:27                                                   */
+    float R[9];          /* camera.h:12  R' = R_i * R_0^T                                 */
+    float R_orig[9];     /* camera.h:13  world->camera rotation before the move           */
+    float R_orig_inv[9]; /* camera.h:14                                                   */
+    float M_inv[9];      /* camera.h:11  inverse of P[:, :3], P = K_0 [R'|t']             */
+    float t4[3];         /* camera.h:15  t'                                               */
+    float P_col34[3];    /* camera.h:9   P[:,3]                                           */
+    float C4[3];         /* camera.h:16  centre of P                                      */
+    float fx, fy, f, alpha, baseline; /* camera.h:17-21 (fx=fy'=K_0 values, alpha=fx/fy)  */
+    float depthMin, depthMax;         /* camera.h:23-28                                   */
+} tsar_camera;
+
+/* Hot fields of AlgorithmParameters (algorithmparameters.h:19-89). */
+typedef struct tsar_params {
+    int box_hsize;        /* :57 window width  (scripts: --blocksize=11)  */
+    int box_vsize;        /* :58 window height                            */
+    int iterations;       /* :64 red/black iterations (8)                 */
+    int n_best;           /* :74                                          */
+    int cost_comb;        /* :75 0 = COMB_ALL, 1 = COMB_BEST_N            */
+    float min_disparity;  /* :56 = f*baseline/depthMax (main.cpp:1393)    */
+    float max_disparity;  /* :55 = f*baseline/depthMin (main.cpp:1396)    */
+    int color_processing; /* :65 must be 0 (float4 textures are not on the north-star path) */
+} tsar_params;
+
+/* gSLICr settings (gSLICr_settings.h:10-21); TSAR's call site: main.cpp:608-615. */
+typedef struct tsar_slic_settings {
+    int img_w, img_h;
+    int spixel_size;             /* 20 */
+    int no_iters;                /* 5  */
+    float coh_weight;            /* 5  */
+    int do_enforce_connectivity; /* 0  */
+    int correct_reduction;       /* 0 = bit-parity with the reference build's partial warp-tail
+                                    reduction; 1 = mathematically complete sums */
+} tsar_slic_settings;
+
+/* Per-pixel / per-region arrays of LineState (linestate.h:10-221) that cross the boundary. */
+typedef enum tsar_field {
+    TSAR_F_NORM4 = 0,        /* float4 lines->norm4  plane (n, d), n.X + d = 0      :12  */
+    TSAR_F_COST = 1,         /* float  lines->c                                      :13  */
+    TSAR_F_DEPTH = 2,        /* float  lines->depth (holds a disparity, sic)         :14  */
+    TSAR_F_FAKEDEPTH = 3,    /* float  lines->fakedepth                              :15  */
+    TSAR_F_SCALE = 4,        /* float  lines->scale   reliable flag                  :33  */
+    TSAR_F_CANNY = 5,        /* float  lines->canny   region label stored as float   :17  */
+    TSAR_F_RATIO = 6,        /* float  lines->ratio                                  :40  */
+    TSAR_F_BEVIEW = 7,       /* int    lines->beview                                 :41  */
+    TSAR_F_LRDIFF = 8,       /* float  lines->lrdiff                                 :42  */
+    TSAR_F_CONFID = 9,       /* float  lines->confid                                 :43  */
+    TSAR_F_REGION_TEXT = 10, /* float  cannylines->text  (-1 = textureless region)   :36  */
+    TSAR_F_REGION_NORM4 = 11 /* float4 cannylines->norm4 per-region plane            :12  */
+} tsar_field;
+
+/* Launch kinds for tsar_launch (single checkerboard half-steps, gipuma.cu:1746-1752). */
+enum { TSAR_BLACK_SPATIAL = 0, TSAR_BLACK_REFINE = 1, TSAR_RED_SPATIAL = 2, TSAR_RED_REFINE = 3 };
+
+typedef struct tsar_ctx tsar_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* Replaces selectCudaDevice + new GlobalState (main.cpp:1230-1266, 1876; globalstate.h:25-54).
+ * `stream` is a cudaStream_t passed as void* (NULL = a private non-blocking stream). */
+int tsar_create(int device, void *stream, tsar_ctx **out);
+int tsar_destroy(tsar_ctx *ctx);
+const char *tsar_last_error(const tsar_ctx *ctx);
+int tsar_sync(tsar_ctx *ctx);
+
+/* ---- inputs ------------------------------------------------------------------------------- */
+/* Replaces addImageToTextureFloatGray + the camera/view-selection fill of runGipuma
+ * (main.cpp:1190-1228, 1316-1385).  images[i] points to W*H float32 grey values (0..255,
+ * main.cpp:1423), image 0 is the reference view; cams[i] likewise.  subset[0..V) are indices of
+ * the selected source views (CameraParameters_cu::viewSelectionSubset, cameraparameters.h:17).
+ * images_on_device != 0 means the pointers are device pointers (no H2D copy). */
+int tsar_set_views(tsar_ctx *ctx, int W, int H, int n_images, const float *const *images,
+                   int images_on_device, const tsar_camera *cams, float cam_f, const int *subset, int V);
+/* Replaces gs->params = &algParams (main.cpp:1408). */
+int tsar_set_params(tsar_ctx *ctx, const tsar_params *p);
+
+/* ---- the PatchMatch path (north-star items 1-3) ---------------------------------------------- */
+/* gipuma_init_cu2 (gipuma.cu:679-729) with curand_init(seed, y, x): same XORWOW streams as the
+ * reference when it is given `seed` in place of clock64(). */
+int tsar_init_planes(tsar_ctx *ctx, uint64_t seed);
+/* Alternative to tsar_init_planes: take the reference's initial planes (host pointers;
+ * norm4 = W*H float4, cost = W*H float or NULL to evaluate the cost of the loaded planes). */
+int tsar_load_planes(tsar_ctx *ctx, const float *norm4, const float *cost);
+/* One checkerboard half-step (gipuma_{black,red}_{spatialProp,planeRefine}_cu, gipuma.cu:1097-1138);
+ * `seed` is used by the refine kinds only. */
+int tsar_launch(tsar_ctx *ctx, int kind, uint64_t seed);
+/* The loop of gipuma_first (gipuma.cu:1744-1754): iters x (black SP, black PR, red SP, red PR).
+ * refine_seeds = 2*iters seeds (black, red per iteration) or NULL for seed0+1+2*it+colour. */
+int tsar_iterate(tsar_ctx *ctx, int iters, uint64_t seed0, const uint64_t *refine_seeds);
+/* pmCostMultiview_cu (gipuma.cu:456-518) for n explicit (pixel, plane) pairs; host pointers:
+ * xy = n int2, planes = n float4, outputs n each (beview/ratio may be NULL). */
+int tsar_eval_planes(tsar_ctx *ctx, int n, const int *xy, const float *planes, float *cost, int *beview,
+                     float *ratio);
+
+/* ---- confidence, TSAR glue and depth completion (north-star item 4) --------------------------- */
+int tsar_lrdiff(tsar_ctx *ctx);          /* gipuma_getlrdiff      gipuma.cu:1161-1186            */
+int tsar_getview(tsar_ctx *ctx);         /* gipuma_getview        gipuma.cu:1189-1213 (sliccuda) */
+int tsar_get_disp(tsar_ctx *ctx);        /* gipuma_get_disp       gipuma.cu:732-755  (firstcuda) */
+int tsar_update_scale_2(tsar_ctx *ctx);  /* gipuma_update_scale_2 gipuma.cu:1262-1292 (fakecuda) */
+int tsar_update_scale(tsar_ctx *ctx);    /* gipuma_update_scale   gipuma.cu:1216-1259 (fillcuda) */
+int tsar_compute_disp(tsar_ctx *ctx);    /* gipuma_compute_disp   gipuma.cu:810-844  (fillcuda)  */
+int tsar_wmf(tsar_ctx *ctx, int iter);        /* gipuma_WMF       gipuma.cu:1500-1698 */
+int tsar_wmf_final(tsar_ctx *ctx, int iter);  /* gipuma_WMF_Final gipuma.cu:1295-1497 */
+/* Region table for the two update_scale kernels (cannylines->text / ->norm4, main.cpp:570-593,
+ * 1722-1729).  Host pointers, n_regions entries. */
+int tsar_set_regions(tsar_ctx *ctx, int n_regions, const float *text, const float *norm4);
+
+/* ---- state transfer --------------------------------------------------------------------------- */
+int tsar_upload(tsar_ctx *ctx, int field, const void *host_src, size_t bytes);
+int tsar_download(tsar_ctx *ctx, int field, void *host_dst, size_t bytes);
+/* Device pointer of a field (for zero-copy consumers such as a fusion stage on the same GPU). */
+int tsar_device_ptr(tsar_ctx *ctx, int field, void **dev_ptr);
+
+/* ---- whole north-star sequence ------------------------------------------------------------------ */
+/* init -> iters x (bSP,bPR,rSP,rPR) -> getlrdiff -> getview -> compute_disp, everything resident.
+ * ms_out (optional) receives the CUDA-event time of the sequence on the context's stream. */
+int tsar_depthmap(tsar_ctx *ctx, uint64_t seed0, float *ms_out);
+/* Host-buffer entry (the e2e path): uploads the views, runs tsar_depthmap, downloads the output
+ * layout of gipuma_compute_disp (norm4_out: xyz = world normal, w = depth; W*H float4) and the
+ * confidence map (W*H float).  Either output may be NULL. */
+int tsar_depthmap_host(tsar_ctx *ctx, int W, int H, int n_images, const float *const *images,
+                       const tsar_camera *cams, float cam_f, const int *subset, int V,
+                       const tsar_params *p, uint64_t seed0, float *norm4_out, float *confid_out);
+
+/* ---- gSLICr (north-star item 4) ------------------------------------------------------------------- */
+/* core_engine::Process_Frame + Get_Seg_Res (gSLICr_core_engine.h:11-33; sequence
+ * gSLICr_seg_engine.cpp:30-46).  bgrx = img_w*img_h uchar4 (x=B,y=G,z=R as load_image fills it);
+ * labels_out = img_w*img_h int32.  Host pointers. */
+int tsar_slic(tsar_ctx *ctx, const unsigned char *bgrx, const tsar_slic_settings *s, int *labels_out);
+
+/* ---- instrumentation --------------------------------------------------------------------------------- */
+/* Kernels launched by this context since creation (or since the last reset). */
+int tsar_launch_count(tsar_ctx *ctx, long long *count, int reset);
+/* pmCost evaluations (plane x source view x window) executed, from the closed form of
+ * BASELINE.md section 3 evaluated with the exact border guards. */
+int tsar_eval_count(tsar_ctx *ctx, int iters, long long *n_evals);
+const char *tsar_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSAR_B200_H */

@@ -1,0 +1,54 @@
+#!/usr/bin/env bash
+# oracle/build_ref.sh -- TEST INFRASTRUCTURE.  Compiles the reference's own CUDA sources, from where
+# they lie (read-only checkout, default /root/reference), into oracle/_ref/*.so.  No reference source
+# is copied into the repository; the only generated source (the 2-line snapshot patch, see
+# ref_driver.cu intervention (v)) lives in a temp dir that is removed after compilation.
+# oracle/_ref/ is git-ignored but travels to the GPU box with gpurun.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${TSAR_REFERENCE_DIR:-/root/reference}"
+OUT="$HERE/_ref"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+if [ ! -f "$REF/gipuma.cu" ]; then
+  echo "[build_ref] reference checkout not found at $REF; keeping prebuilt $OUT" >&2
+  exit 0
+fi
+mkdir -p "$OUT"
+COMMON="-std=c++14 -O3 $ARCH -lineinfo -Xcompiler -fPIC -shared -w -I$HERE/stubs -I$HERE/../include"
+
+stamp() { stat -c '%Y' "$1" 2>/dev/null || echo 0; }
+need() { # need <target> <deps...>
+  local t="$1"; shift
+  [ -f "$t" ] || return 0
+  for d in "$@"; do [ "$(stamp "$d")" -gt "$(stamp "$t")" ] && return 0; done
+  return 1
+}
+
+# 1. as-is reference kernels (default nvcc flags: -fmad=true, as BASELINE.md B-ref-GPU)
+if need "$OUT/libtsar_ref.so" "$HERE/ref_driver.cu" "$REF/gipuma.cu" "$HERE/build_ref.sh" "$HERE/../include/tsar_b200.h"; then
+  echo "[build_ref] libtsar_ref.so"
+  $NVCC $COMMON -I"$REF" "$HERE/ref_driver.cu" -o "$OUT/libtsar_ref.so"
+fi
+
+# 2. snapshot variant: final stores of gipuma_checkerboard_spatialProp_cu redirected
+if need "$OUT/libtsar_ref_snap.so" "$HERE/ref_driver.cu" "$REF/gipuma.cu" "$HERE/build_ref.sh" "$HERE/../include/tsar_b200.h"; then
+  echo "[build_ref] libtsar_ref_snap.so"
+  TMP="$(mktemp -d)"
+  trap 'rm -rf "$TMP"' EXIT
+  # the two lines must be exactly the stores this recipe expects, otherwise fail loudly
+  sed -n '1047p' "$REF/gipuma.cu" | grep -q 'gs.lines->c\[pindex\] = cost_now;'
+  sed -n '1048p' "$REF/gipuma.cu" | grep -q 'gs.lines->norm4\[pindex\] = norm_now;'
+  sed -e '1047s/gs\.lines->c\[pindex\]/gs.lines->ransa[pindex]/' \
+      -e '1048s/gs\.lines->norm4\[pindex\]/gs.lines->resize4[pindex]/' \
+      "$REF/gipuma.cu" > "$TMP/gipuma_snapshot.cu"
+  $NVCC $COMMON -DORACLE_SNAPSHOT -I"$TMP" -I"$REF" "$HERE/ref_driver.cu" -o "$OUT/libtsar_ref_snap.so"
+  rm -rf "$TMP"; trap - EXIT
+fi
+
+# 3. gSLICr reference kernels (gSLICr_seg_engine_GPU.cu unmodified) + restated host sequence
+if [ -f "$HERE/ref_slic_driver.cu" ] && need "$OUT/libgslic_ref.so" "$HERE/ref_slic_driver.cu" "$REF/gSLICr_Lib/engines/gSLICr_seg_engine_GPU.cu" "$HERE/build_ref.sh"; then
+  echo "[build_ref] libgslic_ref.so"
+  $NVCC $COMMON -I"$REF" -I"$REF/gSLICr_Lib" "$HERE/ref_slic_driver.cu" -o "$OUT/libgslic_ref.so"
+fi
+echo "[build_ref] done: $(ls "$OUT")"

@@ -1,0 +1,742 @@
+// context.cu -- host side of the C ABI declared in include/tsar_b200.h.
+//
+// One tsar_ctx owns the device-resident state of one reference view: images (textures for the
+// hardware-filtered source samples + a linear copy of the reference image for the hoisted window
+// terms), cameras, and the LineState arrays of the reference (linestate.h:10-221) as plain device
+// SoA buffers -- no managed memory, no device-wide syncs, everything on one stream.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/tsar_b200.h"
+#include "glue_kernels.cuh"
+#include "pm_launch.h"
+#include "slic_kernels.cuh"
+#include "wmf_kernels.cuh"
+
+using namespace tsar;
+
+struct tsar_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int W = 0, H = 0, n_images = 0, V = 0;
+    bool have_views = false, have_params = false, have_planes = false;
+    std::vector<tsar_camera> cams;
+    float cam_f = 0.f;
+    std::vector<int> subset;
+    tsar_params params{};
+    // images
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> tex;
+    int arr_w = 0, arr_h = 0;
+    float *ref_img = nullptr;
+    cudaTextureObject_t *d_tex = nullptr;
+    CamDev *d_cams = nullptr;
+    // per-pixel state (capacity n_alloc pixels)
+    size_t n_alloc = 0;
+    float4 *plane[2] = {nullptr, nullptr};
+    float *cost[2] = {nullptr, nullptr};
+    int cur[2] = {0, 0};  // buffer holding the live values of colour 0 (black) / 1 (red)
+    float *depth = nullptr, *fakedepth = nullptr, *scale = nullptr, *canny = nullptr, *ratio = nullptr,
+          *lrdiff = nullptr, *confid = nullptr;
+    int *beview = nullptr;
+    float *region_text = nullptr;
+    float4 *region_plane = nullptr;
+    int n_regions = 0;
+    uint32_t *rng = nullptr;
+    size_t rng_alloc = 0;
+    int rng_pitch = 0, rng_len = 0;
+    // scratch for tsar_eval_planes
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    PmConst pm{};
+    PmConst pm_init{};  // init uses box/2 instead of (box-1)/2 (gipuma.cu:693-694)
+    GlueConst glue{};
+    const PmVariant *variant = &pm_variant_generic;       // kernels compiled for this window / combination
+    const PmVariant *variant_init = &pm_variant_generic;
+    long long launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool fused = true;
+    SlicState slic;
+};
+
+#define CK(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            char buf_[512];                                                                         \
+            snprintf(buf_, sizeof(buf_), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            ctx->err = buf_;                                                                        \
+            return TSAR_ERR_CUDA;                                                                   \
+        }                                                                                           \
+    } while (0)
+
+#define FAIL(code, msg)      \
+    do {                     \
+        ctx->err = (msg);    \
+        return (code);       \
+    } while (0)
+
+static const char *kVersion = "tsar_b200 0.1 (sm_100a)";
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+static size_t win_smem_bytes(int nt, int ns) { return (size_t)ns * nt * sizeof(float2) + (size_t)ns * sizeof(float); }
+
+static const PmVariant *pick_variant(const tsar_params &p, bool init) {
+    const int hs = p.box_hsize, vs = p.box_vsize;
+    const int hr = init ? hs / 2 : (hs - 1) / 2, vr = init ? vs / 2 : (vs - 1) / 2;
+    const bool fast_comb = (p.cost_comb == 1 && p.n_best <= 2);
+    if (fast_comb && hr == vr && hr == 5) return &pm_variant_w11;
+    if (fast_comb && hr == vr && hr == 9) return &pm_variant_w19;
+    return &pm_variant_generic;
+}
+
+static void fill_window(PmConst &c, int hs, int vs, bool init) {
+    c.hrad = init ? hs / 2 : (hs - 1) / 2;
+    c.vrad = init ? vs / 2 : (vs - 1) / 2;
+    c.n1x = c.hrad + 1;  // i = -hrad, -hrad+2, ..., <= hrad   (gipuma.cu:259)
+    c.n1y = c.vrad + 1;
+    c.ns = c.n1x * c.n1y;
+}
+
+static int rebuild_constants(tsar_ctx *ctx) {
+    if (!ctx->have_views || !ctx->have_params) return TSAR_OK;
+    PmConst &c = ctx->pm;
+    memset(&c, 0, sizeof(c));
+    const tsar_camera &r = ctx->cams[0];
+    c.W = ctx->W; c.H = ctx->H; c.V = ctx->V;
+    fill_window(c, ctx->params.box_hsize, ctx->params.box_vsize, false);
+    c.n_best = ctx->params.n_best;
+    c.cost_comb = ctx->params.cost_comb;
+    c.y_limit = std::min(ctx->H, 32 * (((ctx->H / 2) + 15) / 16));
+    c.rng_pitch = ctx->rng_pitch;
+    for (int i = 0; i < 9; i++) { c.Kinv[i] = r.K_inv[i]; c.Minv[i] = r.M_inv[i]; }
+    for (int i = 0; i < 3; i++) { c.Pc[i] = r.P_col34[i]; c.C[i] = r.C4[i]; }
+    c.fx = r.fx; c.alpha = r.alpha; c.cx = r.K[2]; c.cy = r.K[5];
+    c.f_params = ctx->cam_f; c.f_cam0 = r.f; c.baseline = r.baseline;
+    c.depthMin = r.depthMin; c.depthMax = r.depthMax;
+    c.min_disp = ctx->params.min_disparity; c.max_disp = ctx->params.max_disparity;
+    for (int i = 0; i < ctx->V; i++) {
+        const int id = ctx->subset[i];
+        const tsar_camera &s = ctx->cams[id];
+        c.tex[i] = ctx->tex[id];
+        c.view_id[i] = id;
+        for (int k = 0; k < 9; k++) { c.view[i].R[k] = s.R[k]; c.view[i].K[k] = s.K[k]; }
+        for (int k = 0; k < 3; k++) c.view[i].t[k] = s.t4[k];
+    }
+    ctx->pm_init = c;
+    fill_window(ctx->pm_init, ctx->params.box_hsize, ctx->params.box_vsize, true);
+    ctx->variant = pick_variant(ctx->params, false);
+    ctx->variant_init = pick_variant(ctx->params, true);
+    if (win_smem_bytes(128, std::max(c.ns, ctx->pm_init.ns)) > 220 * 1024)
+        FAIL(TSAR_ERR_ARG, "window too large for the shared-memory weight table");
+    GlueConst &g = ctx->glue;
+    memset(&g, 0, sizeof(g));
+    g.W = ctx->W; g.H = ctx->H; g.hrad = c.hrad; g.vrad = c.vrad;
+    for (int i = 0; i < 9; i++) {
+        g.Kinv[i] = r.K_inv[i]; g.Minv[i] = r.M_inv[i]; g.Rorig[i] = r.R_orig[i]; g.Rorig_inv[i] = r.R_orig_inv[i];
+    }
+    for (int i = 0; i < 3; i++) { g.Pc[i] = r.P_col34[i]; g.C[i] = r.C4[i]; }
+    g.fx = r.fx; g.alpha = r.alpha; g.cx = r.K[2]; g.cy = r.K[5];
+    g.f_params = ctx->cam_f; g.baseline = r.baseline;
+    g.min_disp = c.min_disp; g.max_disp = c.max_disp; g.depthMin = c.depthMin; g.depthMax = c.depthMax;
+    return TSAR_OK;
+}
+
+static void free_state(tsar_ctx *ctx) {
+    for (int b = 0; b < 2; b++) { cudaFree(ctx->plane[b]); cudaFree(ctx->cost[b]); ctx->plane[b] = nullptr; ctx->cost[b] = nullptr; }
+    cudaFree(ctx->depth); cudaFree(ctx->fakedepth); cudaFree(ctx->scale); cudaFree(ctx->canny);
+    cudaFree(ctx->ratio); cudaFree(ctx->lrdiff); cudaFree(ctx->confid); cudaFree(ctx->beview);
+    ctx->depth = ctx->fakedepth = ctx->scale = ctx->canny = ctx->ratio = ctx->lrdiff = ctx->confid = nullptr;
+    ctx->beview = nullptr;
+    cudaFree(ctx->ref_img); ctx->ref_img = nullptr;
+    ctx->n_alloc = 0;
+}
+
+static void free_images(tsar_ctx *ctx) {
+    for (auto t : ctx->tex) cudaDestroyTextureObject(t);
+    for (auto a : ctx->arrays) cudaFreeArray(a);
+    ctx->tex.clear();
+    ctx->arrays.clear();
+    ctx->arr_w = ctx->arr_h = 0;
+}
+
+static int ensure_state(tsar_ctx *ctx, size_t n) {
+    if (n <= ctx->n_alloc) return TSAR_OK;
+    free_state(ctx);
+    for (int b = 0; b < 2; b++) {
+        CK(cudaMalloc(&ctx->plane[b], n * sizeof(float4)));
+        CK(cudaMalloc(&ctx->cost[b], n * sizeof(float)));
+    }
+    CK(cudaMalloc(&ctx->depth, n * 4)); CK(cudaMalloc(&ctx->fakedepth, n * 4)); CK(cudaMalloc(&ctx->scale, n * 4));
+    CK(cudaMalloc(&ctx->canny, n * 4)); CK(cudaMalloc(&ctx->ratio, n * 4)); CK(cudaMalloc(&ctx->lrdiff, n * 4));
+    CK(cudaMalloc(&ctx->confid, n * 4)); CK(cudaMalloc(&ctx->beview, n * 4));
+    CK(cudaMalloc(&ctx->ref_img, n * 4));
+    ctx->n_alloc = n;
+    return TSAR_OK;
+}
+
+// LineState::resize memsets every array to 0 (linestate.h:73-109)
+static int zero_state(tsar_ctx *ctx) {
+    const size_t n = (size_t)ctx->W * ctx->H;
+    cudaStream_t s = ctx->stream;
+    for (int b = 0; b < 2; b++) { CK(cudaMemsetAsync(ctx->plane[b], 0, n * 16, s)); CK(cudaMemsetAsync(ctx->cost[b], 0, n * 4, s)); }
+    CK(cudaMemsetAsync(ctx->depth, 0, n * 4, s)); CK(cudaMemsetAsync(ctx->fakedepth, 0, n * 4, s));
+    CK(cudaMemsetAsync(ctx->scale, 0, n * 4, s)); CK(cudaMemsetAsync(ctx->canny, 0, n * 4, s));
+    CK(cudaMemsetAsync(ctx->ratio, 0, n * 4, s)); CK(cudaMemsetAsync(ctx->lrdiff, 0, n * 4, s));
+    CK(cudaMemsetAsync(ctx->confid, 0, n * 4, s)); CK(cudaMemsetAsync(ctx->beview, 0, n * 4, s));
+    ctx->cur[0] = ctx->cur[1] = 0;
+    return TSAR_OK;
+}
+
+static int ensure_scratch(tsar_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return TSAR_OK;
+    cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    CK(cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return TSAR_OK;
+}
+
+static int need_ready(tsar_ctx *ctx) {
+    if (!ctx) return TSAR_ERR_ARG;
+    if (!ctx->have_views) FAIL(TSAR_ERR_STATE, "tsar_set_views has not been called");
+    if (!ctx->have_params) FAIL(TSAR_ERR_STATE, "tsar_set_params has not been called");
+    CK(cudaSetDevice(ctx->device));
+    return TSAR_OK;
+}
+
+// both colours back into buffer 0
+static int consolidate(tsar_ctx *ctx) {
+    for (int col = 0; col < 2; col++)
+        if (ctx->cur[col] != 0) {
+            CK(pm_launch_merge_colour(ctx->W, ctx->H, col, ctx->plane[1], ctx->cost[1], ctx->plane[0], ctx->cost[0],
+                                      ctx->stream));
+            ctx->launches++;
+            ctx->cur[col] = 0;
+        }
+    return TSAR_OK;
+}
+
+static int make_rng_table(tsar_ctx *ctx, uint64_t seed) {
+    CK(pm_launch_rng_table(ctx->rng, ctx->rng_pitch, ctx->H, ctx->rng_len, seed, ctx->stream));
+    ctx->launches++;
+    return TSAR_OK;
+}
+
+static int launch_checker(tsar_ctx *ctx, int mode, int colour) {
+    CheckerArgs a;
+    for (int col = 0; col < 2; col++) { a.plane_in[col] = ctx->plane[ctx->cur[col]]; a.cost_in[col] = ctx->cost[ctx->cur[col]]; }
+    const bool sp = (mode & PM_MODE_SP) != 0;
+    const int out = sp ? (ctx->cur[colour] ^ 1) : ctx->cur[colour];
+    a.plane_out = ctx->plane[out];
+    a.cost_out = ctx->cost[out];
+    a.ratio = ctx->ratio;
+    a.beview = ctx->beview;
+    a.rng = ctx->rng;
+    a.colour = colour;
+    CK(ctx->variant->checker(mode, ctx->pm, ctx->ref_img, a, ctx->stream));
+    ctx->launches++;
+    ctx->cur[colour] = out;
+    return TSAR_OK;
+}
+
+// rows beyond the reference's checkerboard grid are never touched by a half-step: make sure the
+// alternate buffer carries them too (they keep their initial values forever)
+static int seed_alt_buffers(tsar_ctx *ctx) {
+    const size_t n = (size_t)ctx->W * ctx->H;
+    if (ctx->pm.y_limit < ctx->H) {
+        CK(cudaMemcpyAsync(ctx->plane[1], ctx->plane[0], n * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->cost[1], ctx->cost[0], n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return TSAR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *tsar_version(void) { return kVersion; }
+
+int tsar_create(int device, void *stream, tsar_ctx **out) {
+    if (!out) return TSAR_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        fprintf(stderr, "[tsar_b200] no usable CUDA device (requested %d of %d); this library has no CPU path\n", device, ndev);
+        return TSAR_ERR_NODEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        fprintf(stderr, "[tsar_b200] device %d is sm_%d%d; this build contains sm_100a code only\n", device, prop.major, prop.minor);
+        return TSAR_ERR_NODEVICE;
+    }
+    tsar_ctx *ctx = new tsar_ctx;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return TSAR_ERR_CUDA; }
+    if (stream) ctx->stream = (cudaStream_t)stream;
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return TSAR_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    const char *uf = getenv("TSAR_B200_UNFUSED");
+    ctx->fused = !(uf && uf[0] == '1');
+    *out = ctx;
+    return TSAR_OK;
+}
+
+int tsar_destroy(tsar_ctx *ctx) {
+    if (!ctx) return TSAR_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_state(ctx);
+    free_images(ctx);
+    cudaFree(ctx->d_tex); cudaFree(ctx->d_cams); cudaFree(ctx->rng); cudaFree(ctx->scratch);
+    cudaFree(ctx->region_text); cudaFree(ctx->region_plane);
+    slic_free(ctx->slic);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return TSAR_OK;
+}
+
+const char *tsar_last_error(const tsar_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int tsar_sync(tsar_ctx *ctx) {
+    if (!ctx) return TSAR_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSAR_OK;
+}
+
+int tsar_set_views(tsar_ctx *ctx, int W, int H, int n_images, const float *const *images, int on_device,
+                   const tsar_camera *cams, float cam_f, const int *subset, int V) {
+    if (!ctx) return TSAR_ERR_ARG;
+    if (W <= 0 || H <= 0 || n_images < 1 || n_images > 512 || !images || !cams) FAIL(TSAR_ERR_ARG, "bad view arguments");
+    if (V < 1 || V > TSAR_MAX_VIEWS || !subset) FAIL(TSAR_ERR_ARG, "number of selected views must be in [1, 32] (pmCostMultiview_cu costVector[32])");
+    for (int i = 0; i < V; i++)
+        if (subset[i] < 0 || subset[i] >= n_images) FAIL(TSAR_ERR_ARG, "view subset index out of range");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)W * H;
+    int rc = ensure_state(ctx, n);
+    if (rc) return rc;
+    // textures: same descriptor as addImageToTextureFloatGray (main.cpp:1190-1228): float, linear
+    // filter, unnormalised coordinates, address mode "wrap" (which the hardware treats as clamp for
+    // unnormalised coordinates) -- identical descriptor => identical sampling
+    if (ctx->arr_w != W || ctx->arr_h != H || (int)ctx->arrays.size() != n_images) {
+        free_images(ctx);
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+        for (int i = 0; i < n_images; i++) {
+            cudaArray_t a;
+            CK(cudaMallocArray(&a, &cd, W, H));
+            ctx->arrays.push_back(a);
+            cudaResourceDesc rd;
+            memset(&rd, 0, sizeof(rd));
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = a;
+            cudaTextureDesc td;
+            memset(&td, 0, sizeof(td));
+            td.addressMode[0] = cudaAddressModeWrap;
+            td.addressMode[1] = cudaAddressModeWrap;
+            td.filterMode = cudaFilterModeLinear;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            cudaTextureObject_t t;
+            CK(cudaCreateTextureObject(&t, &rd, &td, NULL));
+            ctx->tex.push_back(t);
+        }
+        ctx->arr_w = W; ctx->arr_h = H;
+        cudaFree(ctx->d_tex); cudaFree(ctx->d_cams);
+        ctx->d_tex = nullptr; ctx->d_cams = nullptr;
+        CK(cudaMalloc(&ctx->d_tex, n_images * sizeof(cudaTextureObject_t)));
+        CK(cudaMalloc(&ctx->d_cams, n_images * sizeof(CamDev)));
+        CK(cudaMemcpyAsync(ctx->d_tex, ctx->tex.data(), n_images * sizeof(cudaTextureObject_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    for (int i = 0; i < n_images; i++)
+        CK(cudaMemcpy2DToArrayAsync(ctx->arrays[i], 0, 0, images[i], (size_t)W * 4, (size_t)W * 4, H, kind, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ref_img, images[0], n * 4, kind, ctx->stream));
+    ctx->W = W; ctx->H = H; ctx->n_images = n_images; ctx->V = V;
+    ctx->cams.assign(cams, cams + n_images);
+    ctx->cam_f = cam_f;
+    ctx->subset.assign(subset, subset + V);
+    std::vector<CamDev> cd(n_images);
+    for (int i = 0; i < n_images; i++) {
+        for (int k = 0; k < 9; k++) { cd[i].R[k] = cams[i].R[k]; cd[i].K[k] = cams[i].K[k]; }
+        for (int k = 0; k < 3; k++) cd[i].t[k] = cams[i].t4[k];
+    }
+    CK(cudaMemcpyAsync(ctx->d_cams, cd.data(), n_images * sizeof(CamDev), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // cd / caller buffers may go away
+    // XORWOW row table: W draws of offset + head-room for the Marsaglia rejection loop / 4 draws per refine round
+    ctx->rng_len = W + 192;
+    ctx->rng_pitch = (ctx->rng_len + 31) & ~31;
+    const size_t need = (size_t)ctx->rng_pitch * H;
+    if (need > ctx->rng_alloc) {
+        cudaFree(ctx->rng);
+        ctx->rng = nullptr;
+        CK(cudaMalloc(&ctx->rng, need * sizeof(uint32_t)));
+        ctx->rng_alloc = need;
+    }
+    ctx->have_views = true;
+    ctx->have_planes = false;
+    rc = zero_state(ctx);
+    if (rc) return rc;
+    return rebuild_constants(ctx);
+}
+
+int tsar_set_params(tsar_ctx *ctx, const tsar_params *p) {
+    if (!ctx || !p) return TSAR_ERR_ARG;
+    if (p->box_hsize < 1 || p->box_vsize < 1 || p->n_best < 1) FAIL(TSAR_ERR_ARG, "bad window / n_best");
+    if (p->color_processing) FAIL(TSAR_ERR_ARG, "color_processing (float4 textures) is outside the north-star path");
+    ctx->params = *p;
+    ctx->have_params = true;
+    return rebuild_constants(ctx);
+}
+
+int tsar_init_planes(tsar_ctx *ctx, uint64_t seed) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if ((rc = zero_state(ctx))) return rc;
+    if ((rc = make_rng_table(ctx, seed))) return rc;
+    CK(ctx->variant_init->init(ctx->pm_init, ctx->ref_img, ctx->rng, ctx->rng_len, ctx->plane[0], ctx->cost[0], ctx->stream));
+    ctx->launches++;
+    ctx->cur[0] = ctx->cur[1] = 0;
+    ctx->have_planes = true;
+    return seed_alt_buffers(ctx);
+}
+
+int tsar_load_planes(tsar_ctx *ctx, const float *norm4, const float *cost) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (!norm4) FAIL(TSAR_ERR_ARG, "norm4 is null");
+    const size_t n = (size_t)ctx->W * ctx->H;
+    CK(cudaMemcpyAsync(ctx->plane[0], norm4, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    if (cost) CK(cudaMemcpyAsync(ctx->cost[0], cost, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    else {
+        CK(ctx->variant->cost_of_state(ctx->pm, ctx->ref_img, ctx->plane[0], ctx->cost[0], ctx->stream));
+        ctx->launches++;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->cur[0] = ctx->cur[1] = 0;
+    ctx->have_planes = true;
+    return seed_alt_buffers(ctx);
+}
+
+int tsar_launch(tsar_ctx *ctx, int kind, uint64_t seed) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (!ctx->have_planes) FAIL(TSAR_ERR_STATE, "no planes: call tsar_init_planes or tsar_load_planes first");
+    switch (kind) {
+        case TSAR_BLACK_SPATIAL: return launch_checker(ctx, PM_MODE_SP, 0);
+        case TSAR_RED_SPATIAL: return launch_checker(ctx, PM_MODE_SP, 1);
+        case TSAR_BLACK_REFINE:
+            if ((rc = make_rng_table(ctx, seed))) return rc;
+            return launch_checker(ctx, PM_MODE_PR, 0);
+        case TSAR_RED_REFINE:
+            if ((rc = make_rng_table(ctx, seed))) return rc;
+            return launch_checker(ctx, PM_MODE_PR, 1);
+    }
+    FAIL(TSAR_ERR_ARG, "unknown launch kind");
+}
+
+int tsar_iterate(tsar_ctx *ctx, int iters, uint64_t seed0, const uint64_t *refine_seeds) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (!ctx->have_planes) FAIL(TSAR_ERR_STATE, "no planes: call tsar_init_planes or tsar_load_planes first");
+    for (int it = 0; it < iters; it++) {
+        for (int col = 0; col < 2; col++) {
+            const uint64_t seed = refine_seeds ? refine_seeds[2 * it + col] : seed0 + 1 + 2 * (uint64_t)it + col;
+            if (ctx->fused) {
+                // spatial propagation and refinement of one colour in ONE kernel: the refinement of a
+                // pixel depends only on that pixel's own state after propagation
+                if ((rc = make_rng_table(ctx, seed))) return rc;
+                if ((rc = launch_checker(ctx, PM_MODE_FUSED, col))) return rc;
+            } else {
+                if ((rc = launch_checker(ctx, PM_MODE_SP, col))) return rc;
+                if ((rc = make_rng_table(ctx, seed))) return rc;
+                if ((rc = launch_checker(ctx, PM_MODE_PR, col))) return rc;
+            }
+        }
+    }
+    return TSAR_OK;
+}
+
+int tsar_eval_planes(tsar_ctx *ctx, int n, const int *xy, const float *planes, float *cost, int *beview, float *ratio) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (n <= 0 || !xy || !planes || !cost) FAIL(TSAR_ERR_ARG, "bad eval arguments");
+    const size_t bytes = (size_t)n * (8 + 16 + 4 + 4 + 4);
+    if ((rc = ensure_scratch(ctx, bytes))) return rc;
+    unsigned char *base = (unsigned char *)ctx->scratch;
+    float4 *dpl = (float4 *)base;
+    int2 *dxy = (int2 *)(base + (size_t)n * 16);
+    float *dc = (float *)(base + (size_t)n * 24);
+    int *db = (int *)(base + (size_t)n * 28);
+    float *dr = (float *)(base + (size_t)n * 32);
+    CK(cudaMemcpyAsync(dxy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dpl, planes, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->variant->eval(ctx->pm, ctx->ref_img, n, dxy, dpl, dc, db, dr, ctx->stream));
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cost, dc, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (beview) CK(cudaMemcpyAsync(beview, db, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ratio) CK(cudaMemcpyAsync(ratio, dr, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSAR_OK;
+}
+
+#define PX_GRID dim3 b(32, 8), g((ctx->W + 31) / 32, (ctx->H + 7) / 8)
+
+int tsar_lrdiff(tsar_ctx *ctx) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if ((rc = consolidate(ctx))) return rc;
+    PX_GRID;
+    lrdiff_kernel<<<g, b, 0, ctx->stream>>>(ctx->glue, ctx->d_cams, ctx->d_tex, ctx->n_images, ctx->plane[0], ctx->cost[0],
+                                            ctx->beview, ctx->lrdiff);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TSAR_OK;
+}
+
+int tsar_getview(tsar_ctx *ctx) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if ((rc = consolidate(ctx))) return rc;
+    PX_GRID;
+    getview_kernel<<<g, b, 0, ctx->stream>>>(ctx->glue, ctx->plane[0], ctx->cost[0], ctx->lrdiff, ctx->confid, ctx->depth);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TSAR_OK;
+}
+
+int tsar_get_disp(tsar_ctx *ctx) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if ((rc = consolidate(ctx))) return rc;
+    PX_GRID;
+    get_disp_kernel<<<g, b, 0, ctx->stream>>>(ctx->glue, ctx->plane[0], ctx->depth);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->have_planes = true;
+    return seed_alt_buffers(ctx);
+}
+
+int tsar_compute_disp(tsar_ctx *ctx) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if ((rc = consolidate(ctx))) return rc;
+    PX_GRID;
+    compute_disp_kernel<<<g, b, 0, ctx->stream>>>(ctx->glue, ctx->plane[0], ctx->cost[0]);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TSAR_OK;
+}
+
+int tsar_update_scale(tsar_ctx *ctx) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (!ctx->region_text) FAIL(TSAR_ERR_STATE, "tsar_set_regions has not been called");
+    if ((rc = consolidate(ctx))) return rc;
+    PX_GRID;
+    update_scale_kernel<<<g, b, 0, ctx->stream>>>(ctx->glue, ctx->plane[0], ctx->cost[0], ctx->scale, ctx->depth, ctx->canny,
+                                                  ctx->region_text, ctx->region_plane, ctx->n_regions);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TSAR_OK;
+}
+
+int tsar_update_scale_2(tsar_ctx *ctx) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (!ctx->region_text) FAIL(TSAR_ERR_STATE, "tsar_set_regions has not been called");
+    PX_GRID;
+    update_scale_2_kernel<<<g, b, 0, ctx->stream>>>(ctx->glue, ctx->fakedepth, ctx->canny, ctx->region_text,
+                                                    ctx->region_plane, ctx->n_regions);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TSAR_OK;
+}
+
+int tsar_wmf(tsar_ctx *ctx, int iter) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (iter < 0 || iter > 3) FAIL(TSAR_ERR_ARG, "WMF level must be 0..3 (gipuma.cu:1809)");
+    if ((rc = consolidate(ctx))) return rc;
+    rc = wmf_launch(ctx->glue, ctx->tex[0], ctx->plane[0], ctx->depth, ctx->scale, iter, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return rc;
+}
+
+int tsar_wmf_final(tsar_ctx *ctx, int iter) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (iter < 0 || iter > 5) FAIL(TSAR_ERR_ARG, "WMF_Final level must be 0..5 (gipuma.cu:1844)");
+    if (!ctx->region_text) FAIL(TSAR_ERR_STATE, "tsar_set_regions has not been called");
+    if ((rc = consolidate(ctx))) return rc;
+    rc = wmf_final_launch(ctx->glue, ctx->tex[0], ctx->plane[0], ctx->depth, ctx->scale, ctx->canny, ctx->region_text,
+                          ctx->n_regions, iter, ctx->stream);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return rc;
+}
+
+int tsar_set_regions(tsar_ctx *ctx, int n_regions, const float *text, const float *norm4) {
+    if (!ctx || n_regions < 1 || !text || !norm4) return TSAR_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaFree(ctx->region_text); cudaFree(ctx->region_plane);
+    ctx->region_text = nullptr; ctx->region_plane = nullptr;
+    CK(cudaMalloc(&ctx->region_text, (size_t)n_regions * 4));
+    CK(cudaMalloc(&ctx->region_plane, (size_t)n_regions * 16));
+    CK(cudaMemcpyAsync(ctx->region_text, text, (size_t)n_regions * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->region_plane, norm4, (size_t)n_regions * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_regions = n_regions;
+    return TSAR_OK;
+}
+
+static void *field_ptr(tsar_ctx *ctx, int field, size_t *elt, size_t *count) {
+    *count = (size_t)ctx->W * ctx->H;
+    *elt = 4;
+    switch (field) {
+        case TSAR_F_NORM4: *elt = 16; return ctx->plane[0];
+        case TSAR_F_COST: return ctx->cost[0];
+        case TSAR_F_DEPTH: return ctx->depth;
+        case TSAR_F_FAKEDEPTH: return ctx->fakedepth;
+        case TSAR_F_SCALE: return ctx->scale;
+        case TSAR_F_CANNY: return ctx->canny;
+        case TSAR_F_RATIO: return ctx->ratio;
+        case TSAR_F_BEVIEW: return ctx->beview;
+        case TSAR_F_LRDIFF: return ctx->lrdiff;
+        case TSAR_F_CONFID: return ctx->confid;
+        case TSAR_F_REGION_TEXT: *count = ctx->n_regions; return ctx->region_text;
+        case TSAR_F_REGION_NORM4: *count = ctx->n_regions; *elt = 16; return ctx->region_plane;
+    }
+    return nullptr;
+}
+
+int tsar_upload(tsar_ctx *ctx, int field, const void *src, size_t bytes) {
+    if (!ctx || !src) return TSAR_ERR_ARG;
+    if (!ctx->have_views) FAIL(TSAR_ERR_STATE, "tsar_set_views has not been called");
+    CK(cudaSetDevice(ctx->device));
+    if (field == TSAR_F_NORM4 || field == TSAR_F_COST) {
+        int rc = consolidate(ctx);
+        if (rc) return rc;
+    }
+    size_t elt, count;
+    void *p = field_ptr(ctx, field, &elt, &count);
+    if (!p || bytes != elt * count) FAIL(TSAR_ERR_ARG, "field/size mismatch");
+    CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (field == TSAR_F_NORM4) {
+        ctx->have_planes = true;
+        return seed_alt_buffers(ctx);
+    }
+    if (field == TSAR_F_COST) return seed_alt_buffers(ctx);
+    return TSAR_OK;
+}
+
+int tsar_download(tsar_ctx *ctx, int field, void *dst, size_t bytes) {
+    if (!ctx || !dst) return TSAR_ERR_ARG;
+    if (!ctx->have_views) FAIL(TSAR_ERR_STATE, "tsar_set_views has not been called");
+    CK(cudaSetDevice(ctx->device));
+    if (field == TSAR_F_NORM4 || field == TSAR_F_COST) {
+        int rc = consolidate(ctx);
+        if (rc) return rc;
+    }
+    size_t elt, count;
+    void *p = field_ptr(ctx, field, &elt, &count);
+    if (!p || bytes != elt * count) FAIL(TSAR_ERR_ARG, "field/size mismatch");
+    CK(cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSAR_OK;
+}
+
+int tsar_device_ptr(tsar_ctx *ctx, int field, void **dev_ptr) {
+    if (!ctx || !dev_ptr) return TSAR_ERR_ARG;
+    if (field == TSAR_F_NORM4 || field == TSAR_F_COST) {
+        int rc = consolidate(ctx);
+        if (rc) return rc;
+    }
+    size_t elt, count;
+    *dev_ptr = field_ptr(ctx, field, &elt, &count);
+    return *dev_ptr ? TSAR_OK : TSAR_ERR_ARG;
+}
+
+int tsar_depthmap(tsar_ctx *ctx, uint64_t seed0, float *ms_out) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if ((rc = tsar_init_planes(ctx, seed0))) return rc;
+    if ((rc = tsar_iterate(ctx, ctx->params.iterations, seed0, nullptr))) return rc;
+    if ((rc = tsar_lrdiff(ctx))) return rc;
+    if ((rc = tsar_getview(ctx))) return rc;
+    if ((rc = tsar_compute_disp(ctx))) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (ms_out) {
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+    }
+    return TSAR_OK;
+}
+
+int tsar_depthmap_host(tsar_ctx *ctx, int W, int H, int n_images, const float *const *images, const tsar_camera *cams,
+                       float cam_f, const int *subset, int V, const tsar_params *p, uint64_t seed0, float *norm4_out,
+                       float *confid_out) {
+    int rc;
+    if ((rc = tsar_set_views(ctx, W, H, n_images, images, 0, cams, cam_f, subset, V))) return rc;
+    if ((rc = tsar_set_params(ctx, p))) return rc;
+    if ((rc = tsar_depthmap(ctx, seed0, nullptr))) return rc;
+    const size_t n = (size_t)W * H;
+    if (norm4_out) CK(cudaMemcpyAsync(norm4_out, ctx->plane[0], n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (confid_out) CK(cudaMemcpyAsync(confid_out, ctx->confid, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSAR_OK;
+}
+
+int tsar_slic(tsar_ctx *ctx, const unsigned char *bgrx, const tsar_slic_settings *s, int *labels_out) {
+    if (!ctx || !bgrx || !s || !labels_out) return TSAR_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int nl = 0;
+    const char *msg = slic_run(ctx->slic, bgrx, *s, labels_out, ctx->stream, &nl);
+    ctx->launches += nl;
+    if (msg) FAIL(TSAR_ERR_CUDA, msg);
+    return TSAR_OK;
+}
+
+int tsar_launch_count(tsar_ctx *ctx, long long *count, int reset) {
+    if (!ctx || !count) return TSAR_ERR_ARG;
+    *count = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return TSAR_OK;
+}
+
+int tsar_eval_count(tsar_ctx *ctx, int iters, long long *n_evals) {
+    if (!ctx || !n_evals) return TSAR_ERR_ARG;
+    if (!ctx->have_views || !ctx->have_params) FAIL(TSAR_ERR_STATE, "views/params not set");
+    const int W = ctx->W, H = ctx->H, yl = ctx->pm.y_limit;
+    int R = 0;
+    for (float dz = ctx->params.max_disparity * 0.5f; dz >= 0.01f; dz = dz / 10.0f) R++;
+    long long sx = 0, sy = 0;  // direction tests passing their border guards (gipuma.cu:889-1022)
+    for (int x = 0; x < W; x++) sx += (x > 2) + (x < W - 3) + (x > 0) + (x < W - 1);
+    for (int y = 0; y < yl; y++) sy += (y > 2) + (y < H - 3) + (y > 0) + (y < H - 1);
+    const long long prop = (long long)yl * sx + (long long)W * sy;
+    const long long refine = (long long)W * yl * R;
+    *n_evals = (long long)ctx->V * ((long long)W * H + (long long)iters * (prop + refine));
+    return TSAR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+// pm_core.cuh -- device-side building blocks of the PatchMatch depthmap path (sm_100a).
+//
+// What the reference computes (gipuma.cu, file:line in each function) is kept, how it is computed is
+// not:
+//   * every term of the bilateral-NCC window that depends only on the reference image -- the
+//     weights w_k, the products w_k*ref_k, sum(w), sum(w*ref), sum(w*ref^2) -- is computed ONCE per
+//     pixel per launch and staged in shared memory ([sample][thread] float2, conflict-free LDS.64),
+//     instead of once per (plane hypothesis x source view) as pmCost does (gipuma.cu:259-277).  The
+//     per-accumulator summation order is unchanged, so the sums are bit-identical;
+//   * camera constants live in the kernel-parameter constant bank, not behind 8 managed pointers
+//     per camera;
+//   * the 9 + 2*S IEEE divisions per cost evaluation share one refined reciprocal per divisor;
+//   * random numbers come from a per-launch table of the XORWOW output stream of each image row
+//     (curand_init(seed, y, x) == stream of row y advanced x draws), not from a per-pixel
+//     curand_init skip-ahead;
+//   * same-colour neighbours are read from the pre-launch snapshot (deterministic), see DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pm_math.cuh"
+
+namespace tsar {
+
+constexpr int kMaxViews = 32;
+constexpr float kMaxCost = 2.0f;  // config.h:22 MAXCOST
+
+struct ViewC {      // one source view, in the frame of the reference camera
+    float R[9];     // Camera_cu::R
+    float t[3];     // Camera_cu::t4
+    float K[9];     // Camera_cu::K (own intrinsics)
+};
+
+struct PmConst {
+    int W, H, V;
+    int hrad, vrad;        // (box-1)/2, gipuma.cu:858-859
+    int n1x, n1y, ns;      // samples per axis (stride 2) and per window
+    int n_best, cost_comb;
+    int y_limit;           // rows the reference's checkerboard grid reaches (gipuma.cu:1721)
+    int rng_pitch;
+    float Kinv[9];         // cameras[0].K_inv
+    float Minv[9];         // cameras[0].M_inv
+    float Pc[3];           // cameras[0].P_col34
+    float C[3];            // cameras[0].C4
+    float fx, alpha, cx, cy;   // cameras[0].fx, .alpha, .K[2], .K[5]
+    float f_params;        // CameraParameters_cu::f
+    float f_cam0;          // cameras[0].f
+    float baseline;        // cameras[0].baseline
+    float depthMin, depthMax;
+    float min_disp, max_disp;
+    cudaTextureObject_t tex[kMaxViews];  // source view textures, order of viewSelectionSubset
+    int view_id[kMaxViews];              // viewSelectionSubset[i]
+    ViewC view[kMaxViews];
+};
+
+// ---------------------------------------------------------------------------------------------
+// window weights (reference-only part of pmCost, gipuma.cu:247, 259-277)
+// ---------------------------------------------------------------------------------------------
+struct RefStats {
+    float inv;      // 1 / sum(w)
+    float sr;       // sum(w*ref) * inv
+    float var_ref;  // sum(w*ref^2)*inv - sr^2
+};
+
+// spatial term of the bilateral weight: -sqrt(i^2+j^2) / (2*5*5), as compiled: sqrt.rn / -50
+__device__ __forceinline__ float spatial_term(int i, int j) {
+    return fdiv(__fsqrt_rn((float)(i * i + j * j)), -50.0f);
+}
+
+// N1 = samples per axis known at compile time (hRad+1, square window) or 0 for run-time sizes.
+template <int NT, int N1>
+__device__ __forceinline__ RefStats window_weights(const PmConst &c, const float *__restrict__ ref, int x, int y,
+                                                   const float *__restrict__ sp, float2 *__restrict__ wt_thread) {
+    const int W = c.W, H = c.H;
+    // tex2D(l, x+0.5, y+0.5) with unnormalised coords: clamp addressing, exact texel
+    const int xc = min(max(x, 0), W - 1), yc = min(max(y, 0), H - 1);
+    const float cen = __ldg(ref + (size_t)yc * W + xc);
+    float sum_ref = 0.f, sum_rr = 0.f, wsum = 0.f;
+    const int n1x = N1 ? N1 : c.n1x, n1y = N1 ? N1 : c.n1y;
+    const int hrad = N1 ? N1 - 1 : c.hrad, vrad = N1 ? N1 - 1 : c.vrad;
+    int k = 0;
+#pragma unroll
+    for (int ii = 0; ii < n1x; ii++) {
+        const int xi = min(max(x - hrad + 2 * ii, 0), W - 1);
+#pragma unroll
+        for (int jj = 0; jj < n1y; jj++, k++) {
+            const int yj = min(max(y - vrad + 2 * jj, 0), H - 1);
+            const float r = __ldg(ref + (size_t)yj * W + xi);
+            // exp(-spatial/50 - |ref-cen|/18), gipuma.cu:266-268
+            const float w = expf(fsub(sp[k], fdiv(fabsf(fsub(r, cen)), 18.0f)));
+            const float tr = fmul(r, w);
+            sum_ref = fadd(sum_ref, tr);       // gipuma.cu:270
+            sum_rr = ffma(r, tr, sum_rr);      // gipuma.cu:271
+            wsum = fadd(wsum, w);              // gipuma.cu:275
+            wt_thread[k * NT] = make_float2(w, tr);
+        }
+    }
+    RefStats s;
+    s.inv = __frcp_rn(wsum);                               // gipuma.cu:279
+    s.sr = fmul(s.inv, sum_ref);                           // :280
+    s.var_ref = ffma(s.inv, sum_rr, -fmul(s.sr, s.sr));    // :281,286
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plane-induced homography H = K_src (R - t n^T / d) K_ref^-1   (getHomography_cu, gipuma.cu:207-224)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void homography(const PmConst &c, const ViewC &v, const float4 &pl, float *__restrict__ Hm) {
+    const Recip rd = make_recip(pl.w);
+    float A[9];
+    const float n[3] = {pl.x, pl.y, pl.z};
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            A[r * 3 + q] = fsub(v.R[r * 3 + q], div_by(fmul(v.t[r], n[q]), rd));  // outer, /d, R - .
+    float T[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            T[r * 3 + q] = dot3(A[r * 3 + 0], c.Kinv[0 * 3 + q], A[r * 3 + 1], c.Kinv[1 * 3 + q], A[r * 3 + 2],
+                                c.Kinv[2 * 3 + q]);
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+            Hm[r * 3 + q] = dot3(v.K[r * 3 + 0], T[0 * 3 + q], v.K[r * 3 + 1], T[1 * 3 + q], v.K[r * 3 + 2],
+                                 T[2 * 3 + q]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one pmCost (gipuma.cu:230-298) with the reference-only terms hoisted
+// ---------------------------------------------------------------------------------------------
+template <int NT, int N1>
+__device__ __forceinline__ float view_cost(const PmConst &c, int vi, int x, int y, const float4 &pl,
+                                           const float2 *__restrict__ wt_thread, const RefStats &rs) {
+    float Hm[9];
+    homography(c, c.view[vi], pl, Hm);
+    const cudaTextureObject_t tex = c.tex[vi];
+    float s_s = 0.f, s_ss = 0.f, s_rs = 0.f;
+    const int n1x = N1 ? N1 : c.n1x, n1y = N1 ? N1 : c.n1y;
+    const int hrad = N1 ? N1 - 1 : c.hrad, vrad = N1 ? N1 - 1 : c.vrad;
+    int k = 0;
+#pragma unroll
+    for (int ii = 0; ii < n1x; ii++) {
+        const float px = (float)(x - hrad + 2 * ii);
+        const float a0 = fmul(Hm[0], px), a1 = fmul(Hm[3], px), a2 = fmul(Hm[6], px);
+#pragma unroll
+        for (int jj = 0; jj < n1y; jj++, k++) {
+            const float py = (float)(y - vrad + 2 * jj);
+            // H * (px, py, 1): m0*px rounded, m1*py fused, + m2   (config.h matvecmul4noz as compiled)
+            const float X = fadd(Hm[2], ffma(Hm[1], py, a0));
+            const float Y = fadd(Hm[5], ffma(Hm[4], py, a1));
+            const float Z = fadd(Hm[8], ffma(Hm[7], py, a2));
+            const Recip rz = make_recip(Z);
+            const float xs = fadd(div_by(X, rz), 0.5f);
+            const float ys = fadd(div_by(Y, rz), 0.5f);
+            const float src = tex2D<float>(tex, xs, ys);  // hardware bilinear, clamp
+            const float2 w = wt_thread[k * NT];           // (w, w*ref)
+            const float ts = fmul(src, w.x);
+            s_s = fadd(s_s, ts);            // gipuma.cu:272
+            s_ss = ffma(src, ts, s_ss);     // :273
+            s_rs = ffma(src, w.y, s_rs);    // :274
+        }
+    }
+    const float ss = fmul(rs.inv, s_s);
+    const float var_src = ffma(rs.inv, s_ss, -fmul(ss, ss));
+    const float rsn = fmul(rs.inv, s_rs);
+    if (fminf(rs.var_ref, var_src) < 1e-5f) return kMaxCost;  // gipuma.cu:289-291
+    const float covar = ffma(-rs.sr, ss, rsn);
+    const float denom = __fsqrt_rn(fmul(rs.var_ref, var_src));
+    return fmaxf(0.0f, fminf(kMaxCost, fsub(1.0f, fdiv(covar, denom))));  // :295
+}
+
+// ---------------------------------------------------------------------------------------------
+// pmCostMultiview_cu (gipuma.cu:456-518)
+// ---------------------------------------------------------------------------------------------
+struct MvResult {
+    float cost;
+    float ratio;
+    int beview;
+};
+
+// GENERIC = false: only the two smallest costs are ever read (cost_comb == COMB_BEST_N and
+// n_best <= 2, the setting of every run script), kept in registers.  GENERIC = true: any n_best /
+// COMB_ALL through the reference's full insertion sort (local-memory arrays, as the reference).
+template <int NT, int N1, bool GENERIC>
+__device__ __forceinline__ MvResult multiview_cost(const PmConst &c, int x, int y, const float4 &pl,
+                                                   const float2 *__restrict__ wt_thread, const RefStats &rs) {
+    MvResult out;
+    if (!GENERIC) {
+        float s0 = __int_as_float(0x7f800000), s1 = __int_as_float(0x7f800000);
+        int nvalid = 0, bidx = -1;
+        for (int vi = 0; vi < c.V; vi++) {
+            float cv = view_cost<NT, N1>(c, vi, x, y, pl, wt_thread, rs);
+            if (cv < kMaxCost) nvalid++;
+            else cv = kMaxCost;
+            if (cv < s0) { s1 = s0; s0 = cv; bidx = vi; }
+            else {
+                if (cv == s0) bidx = vi;      // "last view whose cost equals the minimum", gipuma.cu:506-510
+                if (cv < s1) s1 = cv;
+            }
+        }
+        const int nb = min(nvalid, c.n_best);
+        if (nb > 0) {
+            out.cost = (nb == 1) ? s0 : fdiv(fadd(s0, s1), 2.0f);
+            out.ratio = fdiv(s0, s1);
+            out.beview = c.view_id[bidx];
+        } else {
+            out.cost = kMaxCost; out.ratio = 0.f; out.beview = -1;
+        }
+        return out;
+    } else {
+        // general combination: full insertion sort as the reference does (sort_small, gipuma.cu:425-434)
+        float cv[kMaxViews], orig[kMaxViews];
+        int nvalid = 0;
+        for (int vi = 0; vi < c.V; vi++) {
+            float v = view_cost<NT, N1>(c, vi, x, y, pl, wt_thread, rs);
+            if (v < kMaxCost) nvalid++;
+            else v = kMaxCost;
+            cv[vi] = v; orig[vi] = v;
+        }
+        for (int i = 1; i < c.V; i++) {
+            float tmp = cv[i];
+            int j = i;
+            for (; j >= 1 && tmp < cv[j - 1]; j--) cv[j] = cv[j - 1];
+            cv[j] = tmp;
+        }
+        int nb = nvalid;
+        if (c.cost_comb == 1) nb = min(nb, c.n_best);
+        if (nb > 0) {
+            float s = 0.f;
+            for (int i = 0; i < nb; i++) s = fadd(s, cv[i]);
+            out.cost = fdiv(s, (float)nb);
+            out.ratio = fdiv(cv[0], cv[1]);
+            out.beview = -1;
+            for (int i = 0; i < c.V; i++) if (cv[0] == orig[i]) out.beview = c.view_id[i];
+        } else {
+            out.cost = kMaxCost; out.ratio = 0.f; out.beview = -1;
+        }
+        return out;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small geometric helpers on the reference camera
+// ---------------------------------------------------------------------------------------------
+// getDepthFromPlane3_cu / getDisparity_cu (gipuma.cu:436-453): depth of plane (n,d) along the ray of (x,y)
+__device__ __forceinline__ float plane_depth(const PmConst &c, const float4 &pl, int x, int y) {
+    if (pl.w != pl.w) return 1000.0f;
+    const float dy = fsub((float)y, c.cy), dx = fsub((float)x, c.cx);
+    const float den = ffma(pl.z, c.fx, ffma(pl.x, dx, fmul(c.alpha, fmul(pl.y, dy))));
+    return fdiv(fmul(pl.w, -c.fx), den);
+}
+
+// getD_cu (gipuma.cu:71-86): plane offset d so that the plane with normal n passes through the
+// point at `depth` on the ray of (x,y)
+__device__ __forceinline__ float plane_d(const PmConst &c, float nx, float ny, float nz, int x, int y, float depth) {
+    const float ptx = ffma((float)x, depth, -c.Pc[0]);
+    const float pty = ffma((float)y, depth, -c.Pc[1]);
+    const float ptz = fsub(depth, c.Pc[2]);
+    float X, Y, Z;
+    matvec3(c.Minv, ptx, pty, ptz, X, Y, Z);
+    return -dot3(nx, X, ny, Y, nz, Z);
+}
+
+// getViewVector_cu (gipuma.cu:97-105)
+__device__ __forceinline__ void view_vector(const PmConst &c, int x, int y, float &vx, float &vy, float &vz) {
+    const float ptx = fsub((float)x, c.Pc[0]), pty = fsub((float)y, c.Pc[1]), ptz = fsub(1.0f, c.Pc[2]);
+    float X, Y, Z;
+    matvec3(c.Minv, ptx, pty, ptz, X, Y, Z);
+    vx = fsub(X, c.C[0]); vy = fsub(Y, c.C[1]); vz = fsub(Z, c.C[2]);
+    const float r = rsqrtf(dot3(vx, vx, vy, vy, vz, vz));  // normalize_cu, gipuma.cu:88-95
+    vx = fmul(vx, r); vy = fmul(vy, r); vz = fmul(vz, r);
+}
+
+// curand_uniform on a raw XORWOW output (curand_uniform.h:69-72): x*2^-32 + 2^-33, fused
+__device__ __forceinline__ float uniform01(uint32_t u) {
+    return ffma(__uint2float_rn(u), __uint_as_float(0x2f800000u), __uint_as_float(0x2f000000u));
+}
+
+}  // namespace tsar

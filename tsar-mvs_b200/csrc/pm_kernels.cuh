@@ -1,0 +1,286 @@
+// pm_kernels.cuh -- __global__ kernels of the PatchMatch path (random init, checkerboard propagation,
+// plane refinement, explicit-plane evaluation, XORWOW row tables).  Instantiated per window variant by pm_inst_*.cu.
+#pragma once
+#include "pm_core.cuh"
+#include "pm_launch.h"
+
+namespace tsar {
+
+// shared memory carve-up common to the window kernels
+template <int NT>
+struct WinSmem {
+    float2 *wt;  // [ns][NT]
+    float *sp;   // [ns]
+    __device__ __forceinline__ WinSmem(unsigned char *base, int ns) {
+        wt = reinterpret_cast<float2 *>(base);
+        sp = reinterpret_cast<float *>(base + (size_t)ns * NT * sizeof(float2));
+    }
+};
+
+template <int N1>
+__device__ __forceinline__ void fill_spatial_table(const PmConst &c, float *sp, int tid, int nthreads) {
+    const int n1y = N1 ? N1 : c.n1y;
+    const int hrad = N1 ? N1 - 1 : c.hrad, vrad = N1 ? N1 - 1 : c.vrad;
+    const int ns = N1 ? N1 * N1 : c.ns;
+    for (int k = tid; k < ns; k += nthreads) {
+        const int ii = k / n1y, jj = k - ii * n1y;
+        sp[k] = spatial_term(-hrad + 2 * ii, -vrad + 2 * jj);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (1) random plane initialisation -- gipuma_init_cu2 (gipuma.cu:679-729)
+// ---------------------------------------------------------------------------------------------
+template <int NT, int MINB, int N1, bool GEN>
+__global__ void __launch_bounds__(NT, MINB) pm_init_kernel(const __grid_constant__ PmConst c, const float *__restrict__ ref,
+                                                     const uint32_t *__restrict__ rng, int rng_len,
+                                                     float4 *__restrict__ plane, float *__restrict__ cost) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WinSmem<NT> sm(smem_raw, N1 ? N1 * N1 : c.ns);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    fill_spatial_table<N1>(c, sm.sp, tid, NT);
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= c.W || y >= c.H) return;
+    float2 *wt = sm.wt + tid;
+    const RefStats rs = window_weights<NT, N1>(c, ref, x, y, sm.sp, wt);
+
+    const uint32_t *row = rng + (size_t)y * c.rng_pitch + x;
+    const int avail = rng_len - x;  // draws available to this pixel
+    float vx, vy, vz;
+    view_vector(c, x, y, vx, vy, vz);
+    // disparity uniform in [min_disparity, max_disparity] (gipuma.cu:709)
+    const float disp = ffma(uniform01(row[0]), fsub(c.max_disp, c.min_disp), c.min_disp);
+    // Marsaglia point on the sphere (gipuma.cu:118-132)
+    float mx, my, sum;
+    int n = 1;
+    do {
+        mx = ffma(uniform01(row[min(n, avail - 1)]), 2.0f, -1.0f);
+        my = ffma(uniform01(row[min(n + 1, avail - 1)]), 2.0f, -1.0f);
+        n += 2;
+        sum = ffma(mx, mx, fmul(my, my));
+    } while (sum >= 1.0f && n + 1 < avail);
+    const float sq = __fsqrt_rn(fsub(1.0f, sum));
+    float nx = fmul(fadd(mx, mx), sq), ny = fmul(fadd(my, my), sq), nz = fsub(1.0f, fadd(sum, sum));
+    if (dot3(nx, vx, ny, vy, nz, vz) > 0.0f) { nx = -nx; ny = -ny; nz = -nz; }  // vecOnHemisphere_cu :106-112
+    const float depth = fdiv(fmul(c.f_cam0, c.baseline), disp);                  // :712
+    float4 pl = make_float4(nx, ny, nz, 0.f);
+    pl.w = plane_d(c, nx, ny, nz, x, y, depth);                                  // :715
+    const MvResult r = multiview_cost<NT, N1, GEN>(c, x, y, pl, wt, rs);
+    const size_t p = (size_t)y * c.W + x;
+    plane[p] = pl;
+    cost[p] = r.cost;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2) red/black checkerboard propagation + plane refinement
+//     gipuma_{black,red}_spatialProp_cu / _planeRefine_cu (gipuma.cu:847-1138)
+// One thread per pixel of the launch's colour; block = 32 columns x (NT/32) row pairs, lane parity
+// selects the row of the pair exactly as the reference's wrappers do (gipuma.cu:1099-1103).
+// State is double buffered per colour: neighbours are read from `*_in` (pre-launch snapshot of both
+// colours), the thread's own result goes to `*_out` (which may alias `*_in` when DO_SP is false).
+// ---------------------------------------------------------------------------------------------
+
+template <int NT, int MINB, int N1, bool GEN, bool DO_SP, bool DO_PR>
+__global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_constant__ PmConst c,
+                                                        const float *__restrict__ ref, const CheckerArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WinSmem<NT> sm(smem_raw, N1 ? N1 * N1 : c.ns);
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    fill_spatial_table<N1>(c, sm.sp, tid, NT);
+    __syncthreads();
+    const int W = c.W, H = c.H;
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = (blockIdx.y * (NT / 32) + threadIdx.y) * 2 + ((x + a.colour) & 1);
+    if (x >= W || y >= H || y >= c.y_limit) return;
+    const int own = a.colour;
+    const int pidx = y * W + x;
+
+    float2 *wt = sm.wt + tid;
+    const RefStats rs = window_weights<NT, N1>(c, ref, x, y, sm.sp, wt);
+
+    // (no dynamic indexing into the by-value argument struct: that would force a local-memory copy)
+    const float *cS = own ? a.cost_in[1] : a.cost_in[0];
+    const float *cO = own ? a.cost_in[0] : a.cost_in[1];
+    const float4 *pS = own ? a.plane_in[1] : a.plane_in[0];
+    const float4 *pO = own ? a.plane_in[0] : a.plane_in[1];
+    float cost_now = cS[pidx];
+    float4 norm_now = pS[pidx];
+    float ratio_now = 0.f;
+    int beview_now = 0;
+    bool meta_dirty = false;
+
+    if (DO_SP) {
+        // evaluate the plane of neighbour `pt` at this pixel (spatialPropagation_cu, gipuma.cu:525-566)
+        auto try_plane = [&](int pt, bool from_own) {
+            const float4 cand = from_own ? pS[pt] : pO[pt];
+            const float dep = plane_depth(c, cand, x, y);
+            if (dep >= c.depthMin && dep <= c.depthMax) {  // the cost has no side effect: skip it when the
+                                                           // depth test would reject the plane anyway
+                const MvResult r = multiview_cost<NT, N1, GEN>(c, x, y, cand, wt, rs);
+                if (r.cost < cost_now) {
+                    cost_now = r.cost; norm_now = cand; ratio_now = r.ratio; beview_now = r.beview;
+                    meta_dirty = true;
+                }
+            }
+        };
+        float cmin;
+        int best;
+        // -- four far strips: 11 samples, stride 2, all of the opposite colour (gipuma.cu:888-950)
+        if (y > 2) {  // up_far
+            best = pidx - 3 * W; cmin = cO[best];
+#pragma unroll
+            for (int i = 1; i < 11; i++)
+                if (y > 2 + 2 * i) { const int pt = pidx - (3 + 2 * i) * W; const float v = cO[pt]; if (v < cmin) { cmin = v; best = pt; } }
+            try_plane(best, false);
+        }
+        if (y < H - 3) {  // down_far: the running minimum starts from c[up_far]; that index is
+                          // out of bounds for y < 3 and reads the zero guard (Q5)
+            cmin = (y >= 3) ? cO[pidx - 3 * W] : 0.0f;
+            best = pidx + 3 * W;
+#pragma unroll
+            for (int i = 1; i < 11; i++)
+                if (y < H - 3 - 2 * i) { const int pt = pidx + (3 + 2 * i) * W; const float v = cO[pt]; if (v < cmin) { cmin = v; best = pt; } }
+            try_plane(best, false);
+        }
+        if (x > 2) {  // left_far
+            best = pidx - 3; cmin = cO[best];
+#pragma unroll
+            for (int i = 1; i < 11; i++)
+                if (x > 2 + 2 * i) { const int pt = pidx - 3 - 2 * i; const float v = cO[pt]; if (v < cmin) { cmin = v; best = pt; } }
+            try_plane(best, false);
+        }
+        if (x < W - 3) {  // right_far: comparison is inverted in the reference (tracks the maximum, Q6)
+            best = pidx + 3; cmin = cO[best];
+#pragma unroll
+            for (int i = 1; i < 11; i++)
+                if (x < W - 3 - 2 * i) { const int pt = pidx + 3 + 2 * i; const float v = cO[pt]; if (cmin < v) { cmin = v; best = pt; } }
+            try_plane(best, false);
+        }
+        // -- four near "V" areas: the direct neighbour (opposite colour) plus same-colour extras
+        //    (gipuma.cu:952-1042); same-colour values come from the pre-launch snapshot
+        bool bown;
+        if (y > 0) {  // up_near
+            best = pidx - W; cmin = cO[best]; bown = false;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                if (y > 1 + i && x > i) { const int pt = pidx - (2 + i) * W - i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+                if (y > 1 + i && x < W - 1 - i) { const int pt = pidx - (2 + i) * W + i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+            }
+            try_plane(best, bown);
+        }
+        if (y < H - 1) {  // down_near
+            best = pidx + W; cmin = cO[best]; bown = false;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                if (y < H - 2 - i && x > i) { const int pt = pidx + (2 + i) * W - i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+                if (y < H - 2 - i && x < W - 1 - i) { const int pt = pidx + (2 + i) * W + i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+            }
+            try_plane(best, bown);
+        }
+        if (x > 0) {  // left_near
+            best = pidx - 1; cmin = cO[best]; bown = false;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                if (x > 1 + i && y > i) { const int pt = pidx - (2 + i) - i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+                if (x > 1 + i && y < H - 1 - i) { const int pt = pidx - (2 + i) + i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+            }
+            try_plane(best, bown);
+        }
+        if (x < W - 1) {  // right_near
+            best = pidx + 1; cmin = cO[best]; bown = false;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                if (x < W - 2 - i && y > i) { const int pt = pidx + (2 + i) - i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+                if (x < W - 2 - i && y < H - 1 - i) { const int pt = pidx + (2 + i) + i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+            }
+            try_plane(best, bown);
+        }
+    }
+
+    if (DO_PR) {
+        // planeRefinement_cu + getRndDispAndUnitVector_cu (gipuma.cu:582-676)
+        float vx, vy, vz;
+        view_vector(c, x, y, vx, vy, vz);
+        float depth_now = plane_depth(c, norm_now, x, y);  // gipuma.cu:1073
+        const uint32_t *row = a.rng + (size_t)y * c.rng_pitch + x;
+        const float fb = fmul(c.baseline, c.f_params);
+        float deltaN = 1.0f;
+        int n = 0;
+        for (float deltaZ = fmul(c.max_disp, 0.5f); deltaZ >= 0.01f; deltaZ = fdiv(deltaZ, 10.0f)) {
+            const float u0 = uniform01(row[n]), u1 = uniform01(row[n + 1]), u2 = uniform01(row[n + 2]),
+                        u3 = uniform01(row[n + 3]);
+            n += 4;
+            const float disp = fdiv(fb, depth_now);                          // :596
+            const float lo = fminf(fadd(c.min_disp, disp), deltaZ);          // = -minDelta, :601
+            const float hi = fminf(fsub(c.max_disp, disp), deltaZ);          // = maxDelta,  :602
+            float nd = fadd(ffma(u0, fadd(lo, hi), -lo), disp);              // disp + between(minDelta,maxDelta)
+            nd = fminf(c.max_disp, fmaxf(c.min_disp, nd));                   // :608
+            const float depth = fdiv(fb, nd);                                // :610
+            const float two = fadd(deltaN, deltaN);
+            float nx = fadd(norm_now.x, ffma(two, u1, -deltaN));             // :613-615
+            float ny = fadd(norm_now.y, ffma(two, u2, -deltaN));
+            float nz = fadd(norm_now.z, ffma(two, u3, -deltaN));
+            const float rn = rsqrtf(dot3(nx, nx, ny, ny, nz, nz));           // normalize_cu
+            nx = fmul(nx, rn); ny = fmul(ny, rn); nz = fmul(nz, rn);
+            if (dot3(vx, nx, vy, ny, vz, nz) > 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
+            float4 cand = make_float4(nx, ny, nz, 0.f);
+            cand.w = plane_d(c, nx, ny, nz, x, y, depth);                    // :654
+            const MvResult r = multiview_cost<NT, N1, GEN>(c, x, y, cand, wt, rs);
+            if (r.cost < cost_now) {                                         // :665 (no depth-range test)
+                cost_now = r.cost; norm_now = cand; depth_now = depth; ratio_now = r.ratio; beview_now = r.beview;
+                meta_dirty = true;
+            }
+            deltaN = fmul(deltaN, 0.25f);
+        }
+    }
+
+    a.cost_out[pidx] = cost_now;
+    a.plane_out[pidx] = norm_now;
+    if (meta_dirty) { a.ratio[pidx] = ratio_now; a.beview[pidx] = beview_now; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (3) multi-view matching cost for explicit (pixel, plane) pairs -- the unit the bench counts
+// ---------------------------------------------------------------------------------------------
+template <int NT, int MINB, int N1, bool GEN>
+__global__ void __launch_bounds__(NT, MINB) pm_eval_kernel(const __grid_constant__ PmConst c, const float *__restrict__ ref,
+                                                     int n, const int2 *__restrict__ xy,
+                                                     const float4 *__restrict__ planes, float *__restrict__ cost,
+                                                     int *__restrict__ beview, float *__restrict__ ratio) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WinSmem<NT> sm(smem_raw, N1 ? N1 * N1 : c.ns);
+    const int tid = threadIdx.x;
+    fill_spatial_table<N1>(c, sm.sp, tid, NT);
+    __syncthreads();
+    const int i = blockIdx.x * NT + tid;
+    if (i >= n) return;
+    const int2 p = xy[i];
+    float2 *wt = sm.wt + tid;
+    const RefStats rs = window_weights<NT, N1>(c, ref, p.x, p.y, sm.sp, wt);
+    const MvResult r = multiview_cost<NT, N1, GEN>(c, p.x, p.y, planes[i], wt, rs);
+    cost[i] = r.cost;
+    beview[i] = r.beview;
+    ratio[i] = r.ratio;
+}
+
+// cost of the planes currently stored (used by tsar_load_planes when no cost is supplied)
+template <int NT, int MINB, int N1, bool GEN>
+__global__ void __launch_bounds__(NT, MINB) pm_cost_of_state_kernel(const __grid_constant__ PmConst c,
+                                                              const float *__restrict__ ref,
+                                                              const float4 *__restrict__ plane,
+                                                              float *__restrict__ cost) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WinSmem<NT> sm(smem_raw, N1 ? N1 * N1 : c.ns);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    fill_spatial_table<N1>(c, sm.sp, tid, NT);
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= c.W || y >= c.H) return;
+    float2 *wt = sm.wt + tid;
+    const RefStats rs = window_weights<NT, N1>(c, ref, x, y, sm.sp, wt);
+    const size_t p = (size_t)y * c.W + x;
+    cost[p] = multiview_cost<NT, N1, GEN>(c, x, y, plane[p], wt, rs).cost;
+}
+
+}  // namespace tsar

@@ -1,0 +1,42 @@
+// pm_launch.h -- host-callable launchers of the PatchMatch kernels, one set per compiled window
+// variant (each variant is its own translation unit so the build parallelises).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pm_core.cuh"
+
+namespace tsar {
+
+struct CheckerArgs {
+    const float4 *plane_in[2];  // [colour] full-size arrays, colour = (x+y)&1
+    const float *cost_in[2];
+    float4 *plane_out;          // own colour
+    float *cost_out;
+    float *ratio;
+    int *beview;
+    const uint32_t *rng;
+    int colour;
+};
+
+enum { PM_MODE_SP = 1, PM_MODE_PR = 2, PM_MODE_FUSED = 3 };
+
+struct PmVariant {
+    const char *name;
+    cudaError_t (*init)(const PmConst &, const float *ref, const uint32_t *rng, int rng_len, float4 *plane,
+                        float *cost, cudaStream_t);
+    cudaError_t (*checker)(int mode, const PmConst &, const float *ref, const CheckerArgs &, cudaStream_t);
+    cudaError_t (*eval)(const PmConst &, const float *ref, int n, const int2 *xy, const float4 *planes, float *cost,
+                        int *beview, float *ratio, cudaStream_t);
+    cudaError_t (*cost_of_state)(const PmConst &, const float *ref, const float4 *plane, float *cost, cudaStream_t);
+};
+
+extern const PmVariant pm_variant_w11;      // 11x11 window (hRad 5, 36 samples), n_best <= 2 / COMB_BEST_N
+extern const PmVariant pm_variant_w19;      // 19x19 window (hRad 9, 100 samples), n_best <= 2 / COMB_BEST_N
+extern const PmVariant pm_variant_generic;  // any window, any combination (run-time loops)
+
+cudaError_t pm_launch_rng_table(uint32_t *table, int pitch, int H, int len, unsigned long long seed, cudaStream_t);
+cudaError_t pm_launch_merge_colour(int W, int H, int colour, const float4 *psrc, const float *csrc, float4 *pdst,
+                                   float *cdst, cudaStream_t);
+
+}  // namespace tsar
