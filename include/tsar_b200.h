@@ -177,6 +177,17 @@ int tsar_launch_count(tsar_ctx *ctx, long long *count, int reset);
  * BASELINE.md section 3 evaluated with the exact border guards. */
 int tsar_eval_count(tsar_ctx *ctx, int iters, long long *n_evals);
 const char *tsar_version(void);
+/* tex2D<float> of image `image` at n unnormalised coordinates (xy = n float2, host): used to
+ * calibrate software models of the texture unit's bilinear filter. */
+int tsar_dbg_tex_sample(tsar_ctx *ctx, int image, int n, const float *xy, float *out);
+/* Issue-rate microbenchmarks on this GPU: out3 = {FP32 FFMA TFLOP/s, MUFU Gop/s, bilinear fp32
+ * texture Gsamples/s}; the measured denominators of the PatchMatch roofline. */
+int tsar_dbg_peaks(tsar_ctx *ctx, float *out3);
+/* Test-only: tsar_eval_planes normally rounds H*(x,y,1) as the reference's real kernels do
+ * (fma(m0,x, m1*y) + m2).  The oracle's stand-alone wrapper kernel around pmCostMultiview_cu is compiled
+ * by nvcc with the loop-hoisted form (fma(m1,y, m0*x) + m2); wrapper_rounding=1 selects that form so the
+ * unit-level test can require bit equality against the wrapper.  Production kernels are unaffected. */
+int tsar_dbg_eval_rounding(tsar_ctx *ctx, int wrapper_rounding);
 
 #ifdef __cplusplus
 }

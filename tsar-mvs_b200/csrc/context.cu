@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/tsar_b200.h"
+#include "debug_kernels.cuh"
 #include "glue_kernels.cuh"
 #include "pm_launch.h"
 #include "slic_kernels.cuh"
@@ -64,6 +65,7 @@ struct tsar_ctx {
     long long launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool fused = true;
+    int eval_wrapper_rounding = 0;  // test-only, see tsar_dbg_eval_rounding
     SlicState slic;
 };
 
@@ -487,7 +489,7 @@ int tsar_eval_planes(tsar_ctx *ctx, int n, const int *xy, const float *planes, f
     float *dr = (float *)(base + (size_t)n * 32);
     CK(cudaMemcpyAsync(dxy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dpl, planes, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
-    CK(ctx->variant->eval(ctx->pm, ctx->ref_img, n, dxy, dpl, dc, db, dr, ctx->stream));
+    CK(ctx->variant->eval(ctx->eval_wrapper_rounding, ctx->pm, ctx->ref_img, n, dxy, dpl, dc, db, dr, ctx->stream));
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(cost, dc, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -736,6 +738,64 @@ int tsar_eval_count(tsar_ctx *ctx, int iters, long long *n_evals) {
     const long long prop = (long long)yl * sx + (long long)W * sy;
     const long long refine = (long long)W * yl * R;
     *n_evals = (long long)ctx->V * ((long long)W * H + (long long)iters * (prop + refine));
+    return TSAR_OK;
+}
+
+// ---- instrumentation (see include/tsar_b200.h) ------------------------------------------------
+int tsar_dbg_tex_sample(tsar_ctx *ctx, int image, int n, const float *xy, float *out) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (image < 0 || image >= ctx->n_images || n <= 0 || !xy || !out) FAIL(TSAR_ERR_ARG, "bad sample arguments");
+    if ((rc = ensure_scratch(ctx, (size_t)n * 12))) return rc;
+    float2 *dxy = (float2 *)ctx->scratch;
+    float *dout = (float *)((unsigned char *)ctx->scratch + (size_t)n * 8);
+    CK(cudaMemcpyAsync(dxy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    dbg_tex_sample_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->tex[image], n, dxy, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSAR_OK;
+}
+
+int tsar_dbg_eval_rounding(tsar_ctx *ctx, int wrapper_rounding) {
+    if (!ctx) return TSAR_ERR_ARG;
+    ctx->eval_wrapper_rounding = wrapper_rounding ? 1 : 0;
+    return TSAR_OK;
+}
+
+int tsar_dbg_peaks(tsar_ctx *ctx, float *out3) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (!out3) return TSAR_ERR_ARG;
+    if ((rc = ensure_scratch(ctx, 64))) return rc;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    float best[3] = {0, 0, 0};
+    for (int rep = 0; rep < 4; rep++) {
+        float ms;
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        dbg_ffma_kernel<<<blocks, threads, 0, ctx->stream>>>((float *)ctx->scratch, iters, 1.0000001f, 1e-9f);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        best[0] = std::max(best[0], (float)((double)blocks * threads * iters * 8 * 8 * 2 / (ms * 1e-3) / 1e12));
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        dbg_mufu_kernel<<<blocks, threads, 0, ctx->stream>>>((float *)ctx->scratch, iters / 4);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        best[1] = std::max(best[1], (float)((double)blocks * threads * (iters / 4) * 8 * 4 / (ms * 1e-3) / 1e9));
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        dbg_tex_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->tex[0], (float *)ctx->scratch, iters / 16, ctx->W, ctx->H);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        best[2] = std::max(best[2], (float)((double)blocks * threads * (iters / 16) * 4 / (ms * 1e-3) / 1e9));
+    }
+    out3[0] = best[0];  // TFLOP/s FP32 FFMA
+    out3[1] = best[1];  // G MUFU ops / s
+    out3[2] = best[2];  // G bilinear fp32 texture samples / s
     return TSAR_OK;
 }
 

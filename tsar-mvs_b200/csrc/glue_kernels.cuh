@@ -64,13 +64,12 @@ __global__ void lrdiff_kernel(const __grid_constant__ GlueConst g, const CamDev 
     // forward homography (same arithmetic as the PatchMatch path)
     float Hm[9];
     {
-        const Recip rd = make_recip(pl.w);
         float A[9], T[9];
         const float n[3] = {pl.x, pl.y, pl.z};
 #pragma unroll
         for (int r = 0; r < 3; r++)
 #pragma unroll
-            for (int q = 0; q < 3; q++) A[r * 3 + q] = fsub(cam.R[r * 3 + q], div_by(fmul(cam.t[r], n[q]), rd));
+            for (int q = 0; q < 3; q++) A[r * 3 + q] = fsub(cam.R[r * 3 + q], fdiv(fmul(cam.t[r], n[q]), pl.w));
 #pragma unroll
         for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -102,17 +101,15 @@ __global__ void lrdiff_kernel(const __grid_constant__ GlueConst g, const CamDev 
     V[6] = ffma(Hm[3], Hm[7], -fmul(Hm[4], Hm[6]));
     V[7] = ffma(Hm[0], Hm[7], -fmul(Hm[1], Hm[6]));
     V[8] = fsub(h04, h13);
-    const Recip rdet = make_recip(det);
-    V[0] = div_by(V[0], rdet);  V[1] = div_by(-V[1], rdet); V[2] = div_by(V[2], rdet);
-    V[3] = div_by(-V[3], rdet); V[4] = div_by(V[4], rdet);  V[5] = div_by(-V[5], rdet);
-    V[6] = div_by(V[6], rdet);  V[7] = div_by(-V[7], rdet); V[8] = div_by(V[8], rdet);
+    V[0] = fdiv(V[0], det);  V[1] = fdiv(-V[1], det); V[2] = fdiv(V[2], det);
+    V[3] = fdiv(-V[3], det); V[4] = fdiv(V[4], det);  V[5] = fdiv(-V[5], det);
+    V[6] = fdiv(V[6], det);  V[7] = fdiv(-V[7], det); V[8] = fdiv(V[8], det);
 
     // centre of the window in the source view
     const float fx0 = (float)x, fy0 = (float)y;
     const float cz = fadd(ffma(Hm[6], fx0, fmul(Hm[7], fy0)), Hm[8]);
-    const Recip rcz = make_recip(cz);
-    const float pcx = div_by(fadd(ffma(Hm[0], fx0, fmul(Hm[1], fy0)), Hm[2]), rcz);
-    const float pcy = div_by(fadd(ffma(Hm[3], fx0, fmul(Hm[4], fy0)), Hm[5]), rcz);
+    const float pcx = fdiv(fadd(ffma(Hm[0], fx0, fmul(Hm[1], fy0)), Hm[2]), cz);
+    const float pcy = fdiv(fadd(ffma(Hm[3], fx0, fmul(Hm[4], fy0)), Hm[5]), cz);
     const cudaTextureObject_t tl = tex[0], tr = tex[to];
     const float cen = tex2D<float>(tr, fadd(pcx, 0.5f), fadd(pcy, 0.5f));
 
@@ -125,9 +122,8 @@ __global__ void lrdiff_kernel(const __grid_constant__ GlueConst g, const CamDev 
             const float fply = (float)ply;
             const float ref_pix = tex2D<float>(tr, fadd(fplx, 0.5f), fadd(fply, 0.5f));
             const float Z = fadd(ffma(V[6], fplx, fmul(V[7], fply)), V[8]);
-            const Recip rz = make_recip(Z);
-            const float X = div_by(fadd(ffma(V[0], fplx, fmul(V[1], fply)), V[2]), rz);
-            const float Y = div_by(fadd(ffma(V[3], fplx, fmul(V[4], fply)), V[5]), rz);
+            const float X = fdiv(fadd(ffma(V[0], fplx, fmul(V[1], fply)), V[2]), Z);
+            const float Y = fdiv(fadd(ffma(V[3], fplx, fmul(V[4], fply)), V[5]), Z);
             const float src_pix = tex2D<float>(tl, fadd(X, 0.5f), fadd(Y, 0.5f));
             const float w = expf(fsub(spatial_term(i, j), fdiv(fabsf(fsub(ref_pix, cen)), 18.0f)));
             const float wr = fmul(ref_pix, w), ws = fmul(src_pix, w);

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------
 // (3) multi-view matching cost for explicit (pixel, plane) pairs -- the unit the bench counts
 // ---------------------------------------------------------------------------------------------
-template <int NT, int MINB, int N1, bool GEN>
+template <int NT, int MINB, int N1, bool GEN, bool PXF>
 __global__ void __launch_bounds__(NT, MINB) pm_eval_kernel(const __grid_constant__ PmConst c, const float *__restrict__ ref,
                                                      int n, const int2 *__restrict__ xy,
                                                      const float4 *__restrict__ planes, float *__restrict__ cost,
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_eval_kernel(const __grid_constant
     const int2 p = xy[i];
     float2 *wt = sm.wt + tid;
     const RefStats rs = window_weights<NT, N1>(c, ref, p.x, p.y, sm.sp, wt);
-    const MvResult r = multiview_cost<NT, N1, GEN>(c, p.x, p.y, planes[i], wt, rs);
+    const MvResult r = multiview_cost<NT, N1, GEN, PXF>(c, p.x, p.y, planes[i], wt, rs);
     cost[i] = r.cost;
     beview[i] = r.beview;
     ratio[i] = r.ratio;

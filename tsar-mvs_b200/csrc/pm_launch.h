@@ -26,7 +26,7 @@ struct PmVariant {
     cudaError_t (*init)(const PmConst &, const float *ref, const uint32_t *rng, int rng_len, float4 *plane,
                         float *cost, cudaStream_t);
     cudaError_t (*checker)(int mode, const PmConst &, const float *ref, const CheckerArgs &, cudaStream_t);
-    cudaError_t (*eval)(const PmConst &, const float *ref, int n, const int2 *xy, const float4 *planes, float *cost,
+    cudaError_t (*eval)(int wrapper_rounding, const PmConst &, const float *ref, int n, const int2 *xy, const float4 *planes, float *cost,
                         int *beview, float *ratio, cudaStream_t);
     cudaError_t (*cost_of_state)(const PmConst &, const float *ref, const float4 *plane, float *cost, cudaStream_t);
 };

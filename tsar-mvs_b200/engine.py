@@ -1,0 +1,209 @@
+"""Host-side mirror of the reference's depthmap entry points on top of the C ABI.
+
+`DepthmapEngine` is what a user of the reference's firstcuda/sliccuda/fakecuda/fillcuda
+(gipuma.h:2-5) + gSLICr core_engine (gSLICr_core_engine.h:11-33) drives instead; method names follow
+the reference kernels they stand for.  All compute happens in libtsar_b200.so (hand-written sm_100a
+CUDA); this module only marshals numpy arrays / device pointers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+FIELD_DTYPE = {
+    L.F_NORM4: (np.float32, 4), L.F_COST: (np.float32, 1), L.F_DEPTH: (np.float32, 1),
+    L.F_FAKEDEPTH: (np.float32, 1), L.F_SCALE: (np.float32, 1), L.F_CANNY: (np.float32, 1),
+    L.F_RATIO: (np.float32, 1), L.F_BEVIEW: (np.int32, 1), L.F_LRDIFF: (np.float32, 1),
+    L.F_CONFID: (np.float32, 1), L.F_REGION_TEXT: (np.float32, 1), L.F_REGION_NORM4: (np.float32, 4),
+}
+
+
+class TsarError(RuntimeError):
+    pass
+
+
+def make_params(box=11, iterations=8, n_best=1, cost_comb=1, min_disparity=0.0, max_disparity=256.0):
+    """AlgorithmParameters as the run scripts set them (scripts/pipes.sh:10-15)."""
+    return L.TsarParams(box, box, iterations, n_best, cost_comb, min_disparity, max_disparity, 0)
+
+
+def cameras_to_struct(cams):
+    """cams: list of dicts with the tsar_camera fields (see scene.make_cameras)."""
+    arr = (L.TsarCamera * len(cams))()
+    for i, c in enumerate(cams):
+        for name in ("K", "K_inv", "R", "R_orig", "R_orig_inv", "M_inv"):
+            getattr(arr[i], name)[:] = [float(v) for v in np.asarray(c[name], np.float32).reshape(9)]
+        for name in ("t4", "P_col34", "C4"):
+            getattr(arr[i], name)[:] = [float(v) for v in np.asarray(c[name], np.float32).reshape(3)]
+        for name in ("fx", "fy", "f", "alpha", "baseline", "depthMin", "depthMax"):
+            setattr(arr[i], name, float(np.float32(c[name])))
+    return arr
+
+
+class DepthmapEngine:
+    """One reference view in flight on one GPU (reference: one gipuma process per view)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = L.load()
+        h = C.c_void_p()
+        rc = self.lib.tsar_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise TsarError(f"tsar_create(device={device}) failed with {rc}: no usable sm_100 GPU (there is no CPU path)")
+        self.h = h
+        self.W = self.H = 0
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tsar_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise TsarError(f"{what} failed ({rc}): {self.lib.tsar_last_error(self.h).decode()}")
+
+    # -- inputs ----------------------------------------------------------------------------------
+    def set_views(self, images, cams, subset, cam_f=None):
+        """images: [n][H][W] float32 numpy (host) -- image 0 is the reference view."""
+        imgs = [np.ascontiguousarray(im, np.float32) for im in images]
+        H, W = imgs[0].shape
+        ptrs = (C.c_void_p * len(imgs))(*[im.ctypes.data for im in imgs])
+        cs = cameras_to_struct(cams) if not isinstance(cams, C.Array) else cams
+        sub = (C.c_int * len(subset))(*[int(s) for s in subset])
+        f = float(cam_f if cam_f is not None else cs[0].f)
+        self._ck(self.lib.tsar_set_views(self.h, W, H, len(imgs), ptrs, 0, cs, f, sub, len(subset)), "tsar_set_views")
+        self.W, self.H = W, H
+        self._keep = (imgs, cs, sub)
+
+    def set_views_device(self, dev_ptrs, W, H, cams, subset, cam_f=None):
+        """Same, from device pointers (e.g. torch tensors already resident in HBM)."""
+        ptrs = (C.c_void_p * len(dev_ptrs))(*[int(p) for p in dev_ptrs])
+        cs = cameras_to_struct(cams) if not isinstance(cams, C.Array) else cams
+        sub = (C.c_int * len(subset))(*[int(s) for s in subset])
+        f = float(cam_f if cam_f is not None else cs[0].f)
+        self._ck(self.lib.tsar_set_views(self.h, W, H, len(dev_ptrs), ptrs, 1, cs, f, sub, len(subset)), "tsar_set_views")
+        self.W, self.H = W, H
+        self._keep = (cs, sub)
+
+    def set_params(self, params):
+        self.params = params
+        self._ck(self.lib.tsar_set_params(self.h, C.byref(params)), "tsar_set_params")
+
+    def set_regions(self, text, norm4):
+        text = np.ascontiguousarray(text, np.float32)
+        norm4 = np.ascontiguousarray(norm4, np.float32).reshape(-1, 4)
+        self._ck(self.lib.tsar_set_regions(self.h, len(text), text.ctypes.data, norm4.ctypes.data), "tsar_set_regions")
+
+    # -- PatchMatch path ---------------------------------------------------------------------------
+    def init_planes(self, seed):                      # gipuma_init_cu2
+        self._ck(self.lib.tsar_init_planes(self.h, int(seed)), "tsar_init_planes")
+
+    def load_planes(self, norm4, cost=None):
+        norm4 = np.ascontiguousarray(norm4, np.float32)
+        cost = None if cost is None else np.ascontiguousarray(cost, np.float32)
+        self._ck(self.lib.tsar_load_planes(self.h, norm4.ctypes.data, cost.ctypes.data if cost is not None else None),
+                 "tsar_load_planes")
+
+    def launch(self, kind, seed=0):                   # one checkerboard half-step
+        self._ck(self.lib.tsar_launch(self.h, int(kind), int(seed)), "tsar_launch")
+
+    def iterate(self, iters, seed0, refine_seeds=None):
+        arr = None
+        if refine_seeds is not None:
+            arr = (C.c_uint64 * len(refine_seeds))(*[int(s) for s in refine_seeds])
+        self._ck(self.lib.tsar_iterate(self.h, int(iters), int(seed0), arr), "tsar_iterate")
+
+    def eval_planes(self, xy, planes, wrapper_rounding=False):   # pmCostMultiview_cu on explicit pairs
+        self._ck(self.lib.tsar_dbg_eval_rounding(self.h, int(bool(wrapper_rounding))), "tsar_dbg_eval_rounding")
+        xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+        planes = np.ascontiguousarray(planes, np.float32).reshape(-1, 4)
+        n = len(xy)
+        cost = np.empty(n, np.float32)
+        bv = np.empty(n, np.int32)
+        ratio = np.empty(n, np.float32)
+        self._ck(self.lib.tsar_eval_planes(self.h, n, xy.ctypes.data, planes.ctypes.data, cost.ctypes.data,
+                                           bv.ctypes.data, ratio.ctypes.data), "tsar_eval_planes")
+        return cost, bv, ratio
+
+    def lrdiff(self): self._ck(self.lib.tsar_lrdiff(self.h), "tsar_lrdiff")                      # gipuma_getlrdiff
+    def getview(self): self._ck(self.lib.tsar_getview(self.h), "tsar_getview")                   # gipuma_getview
+    def get_disp(self): self._ck(self.lib.tsar_get_disp(self.h), "tsar_get_disp")                # gipuma_get_disp
+    def update_scale_2(self): self._ck(self.lib.tsar_update_scale_2(self.h), "tsar_update_scale_2")
+    def update_scale(self): self._ck(self.lib.tsar_update_scale(self.h), "tsar_update_scale")
+    def compute_disp(self): self._ck(self.lib.tsar_compute_disp(self.h), "tsar_compute_disp")
+    def wmf(self, it): self._ck(self.lib.tsar_wmf(self.h, int(it)), "tsar_wmf")
+    def wmf_final(self, it): self._ck(self.lib.tsar_wmf_final(self.h, int(it)), "tsar_wmf_final")
+
+    def depthmap(self, seed0, timed=True):
+        """init -> iterations -> lrdiff -> getview -> compute_disp, resident. Returns CUDA-event ms."""
+        ms = C.c_float(0)
+        self._ck(self.lib.tsar_depthmap(self.h, int(seed0), C.byref(ms) if timed else None), "tsar_depthmap")
+        return ms.value
+
+    def depthmap_host(self, images, cams, subset, params, seed0, want_norm4=True, want_confid=True, cam_f=None,
+                      out_norm4=None, out_confid=None):
+        """The end-to-end call: host images in, host depth/normal/confidence out."""
+        imgs = [np.ascontiguousarray(im, np.float32) for im in images]
+        H, W = imgs[0].shape
+        ptrs = (C.c_void_p * len(imgs))(*[im.ctypes.data for im in imgs])
+        cs = cameras_to_struct(cams) if not isinstance(cams, C.Array) else cams
+        sub = (C.c_int * len(subset))(*[int(s) for s in subset])
+        f = float(cam_f if cam_f is not None else cs[0].f)
+        if out_norm4 is None and want_norm4:
+            out_norm4 = np.empty((H, W, 4), np.float32)
+        if out_confid is None and want_confid:
+            out_confid = np.empty((H, W), np.float32)
+        self._ck(self.lib.tsar_depthmap_host(self.h, W, H, len(imgs), ptrs, cs, f, sub, len(subset), C.byref(params),
+                                             int(seed0), out_norm4.ctypes.data if out_norm4 is not None else None,
+                                             out_confid.ctypes.data if out_confid is not None else None),
+                 "tsar_depthmap_host")
+        self.W, self.H = W, H
+        self.params = params
+        return out_norm4, out_confid
+
+    # -- state -----------------------------------------------------------------------------------
+    def download(self, field, n_regions=None):
+        dt, ch = FIELD_DTYPE[field]
+        if field in (L.F_REGION_TEXT, L.F_REGION_NORM4):
+            shape = (n_regions,) if ch == 1 else (n_regions, ch)
+        else:
+            shape = (self.H, self.W) if ch == 1 else (self.H, self.W, ch)
+        out = np.empty(shape, dt)
+        self._ck(self.lib.tsar_download(self.h, field, out.ctypes.data, out.nbytes), "tsar_download")
+        return out
+
+    def upload(self, field, arr):
+        dt, _ = FIELD_DTYPE[field]
+        arr = np.ascontiguousarray(arr, dt)
+        self._ck(self.lib.tsar_upload(self.h, field, arr.ctypes.data, arr.nbytes), "tsar_upload")
+
+    def sync(self):
+        self._ck(self.lib.tsar_sync(self.h), "tsar_sync")
+
+    def launch_count(self, reset=False):
+        n = C.c_longlong(0)
+        self._ck(self.lib.tsar_launch_count(self.h, C.byref(n), int(reset)), "tsar_launch_count")
+        return n.value
+
+    def eval_count(self, iters):
+        n = C.c_longlong(0)
+        self._ck(self.lib.tsar_eval_count(self.h, int(iters), C.byref(n)), "tsar_eval_count")
+        return n.value
+
+    # -- gSLICr ------------------------------------------------------------------------------------
+    def slic(self, bgrx, spixel_size=20, no_iters=5, coh_weight=5.0, enforce_connectivity=False,
+             correct_reduction=False):
+        """core_engine::Process_Frame + Get_Seg_Res. bgrx: [h][w][4] uint8 (B,G,R,x). Returns int32 labels."""
+        bgrx = np.ascontiguousarray(bgrx, np.uint8)
+        h, w = bgrx.shape[:2]
+        s = L.TsarSlicSettings(w, h, spixel_size, no_iters, coh_weight, int(enforce_connectivity), int(correct_reduction))
+        labels = np.empty((h, w), np.int32)
+        self._ck(self.lib.tsar_slic(self.h, bgrx.ctypes.data, C.byref(s), labels.ctypes.data), "tsar_slic")
+        return labels
