@@ -1,0 +1,373 @@
+#!/usr/bin/env python3
+"""bench.py -- depthmaps/s of the TSAR-MVS per-reference-view depthmap path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one reference view of a synthetic scene of the named shape
+(BASELINE.json configs; default C2 = ETH3D-pipes-shaped 3100x2050, 10 source views, full TSAR path):
+  gSLICr segmentation -> random plane init -> 8 x red/black (propagation + refinement) -> left/right
+  cost check -> confidence -> textureless-region depth completion (update_scale_2, update_scale) ->
+  output layout (compute_disp).
+`value` times that with every input resident in HBM; `e2e` times the same work through the public host
+API (host images in, host depth/normal/confidence/labels out, copies inside the timed region).
+Reference views are independent: with N GPUs each rank processes its own reference views (weak scaling,
+no collective on the data path).
+
+--impl reference runs the reference's own CUDA kernels rebuilt for sm_100 (oracle/_ref: gipuma.cu and
+gSLICr unmodified, managed memory and a device sync after every kernel, as the reference is written) on
+the same workload.  The reference has no CPU implementation of this path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+SEED = 20240601
+FLOPS_PER_EVAL = 1590.0      # 40*S + 150 at S = 36 (as written in pmCost)
+FLOPS_PER_EVAL_19 = 4150.0   # S = 100
+FP32_NOMINAL_TFLOPS = 74.5   # 148 SM x 128 lanes x 2 x 1.965 GHz
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = max(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows if len(r) > 3 + k)]
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.rows),
+                "power_w_max": max(pw) if pw else None}
+
+
+def dist_setup(n_gpus):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    import torch
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def workload_name(cfg_name, cfg, iters):
+    return (f"{cfg_name}: synthetic ETH3D-shaped scene {cfg['W']}x{cfg['H']}, {cfg['V']} source views, one reference view per step, "
+            f"blocksize 11, {iters} iterations, n_best 1; full TSAR path (gSLICr + checkerboard PatchMatch + L/R check + "
+            f"confidence + textureless depth completion)")
+
+
+def build_scene(pkg, cfg_name, rank, device):
+    import torch
+    scene = pkg.scene.make_scene(cfg_name, with_colour=True, ref_index=rank, backend="torch", device=device)
+    imgs_dev = [im.contiguous() for im in scene["images"]]
+    imgs_host = [torch.empty(im.shape, dtype=torch.float32).pin_memory() for im in imgs_dev]
+    for h, d in zip(imgs_host, imgs_dev):
+        h.copy_(d)
+    bgrx = pkg.scene.box_downsample4(scene["bgr"])
+    return scene, imgs_dev, imgs_host, bgrx
+
+
+def cpu_baseline(pkg, cfg, evals_per_depthmap):
+    """Single-threaded C restatement of cost + propagation + refinement (oracle/oracle_cpu.c) on a bounded
+    sample: a 128x96 scene with the config's number of source views, init + 1 iteration."""
+    from oracle import cpu_binding as cb
+    from tsar_mvs_b200.engine import cameras_to_struct
+    small = dict(W=128, H=96, n_images=cfg["V"] + 1, V=cfg["V"], fx=cfg["fx"] * 128.0 / cfg["W"], radius=cfg["radius"],
+                 arc_deg=cfg["arc_deg"])
+    sc = pkg.scene.make_scene(small)
+    params = pkg.make_params(box=11, iterations=1, min_disparity=sc["min_disparity"], max_disparity=sc["max_disparity"])
+    o = cb.CpuOracle(pkg._lib.TsarCamera, pkg._lib.TsarParams, sc["images"], cameras_to_struct(sc["cams"]), sc["subset"], params, sc["cam_f"])
+    t = time.time()
+    o.init_planes(SEED)
+    o.iterate(1, SEED)
+    dt = time.time() - t
+    ev = o.evals()
+    o.close()
+    return {"value": (ev / dt) / evals_per_depthmap, "unit": "depthmaps/s", "cores": 1, "kind": "port",
+            "sample": f"128x96 scene, V={cfg['V']}, init + 1 red/black iteration = {ev} pmCost evaluations in {dt:.1f} s "
+                      f"({ev / dt / 1e6:.3f} M evals/s), scaled by {evals_per_depthmap} evaluations per depthmap",
+            "host_cores_available": os.cpu_count()}
+
+
+def run_ours(args):
+    import torch
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    L = pkg._lib
+    rank, world, local = dist_setup(args.gpus)
+    cfg = pkg.scene.CONFIGS[args.config]
+    iters = 8
+    scene, imgs_dev, imgs_host, bgrx = build_scene(pkg, args.config, rank, f"cuda:{local}")
+    W, H, V = cfg["W"], cfg["H"], cfg["V"]
+    params = pkg.make_params(box=11, iterations=iters, n_best=1, cost_comb=1, min_disparity=scene["min_disparity"],
+                             max_disparity=scene["max_disparity"])
+    # our kernels run on a torch side stream made current below, so torch.cuda.Event brackets exactly them
+    tstream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(tstream)
+    eng = pkg.DepthmapEngine(local, stream=tstream.cuda_stream)
+    from tsar_mvs_b200.engine import cameras_to_struct
+    cams = cameras_to_struct(scene["cams"])
+    eng.set_views_device([t.data_ptr() for t in imgs_dev], W, H, cams, scene["subset"], cam_f=scene["cam_f"])
+    eng.set_params(params)
+    eng.set_regions(scene["region_text"], scene["region_norm4"])
+    canny = scene["canny"]
+    eng.upload(L.F_CANNY, canny)            # region labels of the reference view (caller input, resident)
+
+    def step_resident(seed):
+        eng.slic(bgrx)                      # quarter-resolution colour image of the reference view
+        eng.init_planes(seed)
+        eng.iterate(iters, seed)
+        eng.lrdiff(); eng.getview()
+        eng.update_scale_2(); eng.update_scale(); eng.compute_disp()
+
+    n_evals = eng.eval_count(iters)
+    for _ in range(args.warmup):
+        step_resident(SEED)
+    eng.launch_count(reset=True)
+    eng.profile(True)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for k in range(args.steps):
+            step_resident(SEED + 100 * k)
+        e1.record()
+        torch.cuda.synchronize()
+    ms_local = e0.elapsed_time(e1)
+    barrier(world)
+    ms = max_over_ranks(ms_local, world)
+    launches = eng.launch_count(reset=True)
+    chk_ms, chk_n = eng.profile_read()
+    eng.profile(False)
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host API: pinned host images in, host results out, every step
+    out_n4 = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    out_cf = torch.empty((H, W), dtype=torch.float32).pin_memory()
+    host_np = [t.numpy() for t in imgs_host]
+
+    def step_e2e(seed):
+        labels = eng.slic(bgrx)
+        eng.set_views(host_np, cams, scene["subset"], cam_f=scene["cam_f"])  # H2D of every view
+        eng.upload(L.F_CANNY, canny)
+        eng.init_planes(seed)
+        eng.iterate(iters, seed)
+        eng.lrdiff(); eng.getview()
+        eng.update_scale_2(); eng.update_scale(); eng.compute_disp()
+        eng.lib.tsar_download(eng.h, L.F_NORM4, out_n4.numpy().ctypes.data, out_n4.numel() * 4)   # D2H
+        eng.lib.tsar_download(eng.h, L.F_CONFID, out_cf.numpy().ctypes.data, out_cf.numel() * 4)
+        return labels
+
+    step_e2e(SEED)
+    barrier(world)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_e2e(SEED + 100 * k)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    h2d = (V + 1) * W * H * 4 + bgrx.nbytes + canny.nbytes
+    d2h = W * H * 20 + bgrx.shape[0] * bgrx.shape[1] * 4
+    e2e = {"value": world * args.steps / e2e_s, "unit": "depthmaps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (fused checkerboard propagation + refinement), timed live with CUDA events
+    ffma_tf, mufu_g, tex_g = eng.peaks()
+    evals_checker = (n_evals - V * W * H) / (2.0 * iters)           # pmCost evaluations per checkerboard launch
+    avg_ms = chk_ms / max(chk_n, 1)
+    achieved = evals_checker * FLOPS_PER_EVAL / (avg_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_dram_bytes.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.config)
+        except Exception:
+            traffic = None
+    peaks_file = {}
+    try:
+        peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
+    alg_bytes = (W * H / 2.0) * (4 * (1 + V) * 4 + 40)               # compulsory bytes of one launch
+    roofline = {
+        "bound": "fp32", "kernel": "pm_checker_kernel (fused red/black propagation + refinement)",
+        "achieved": achieved, "peak": ffma_tf, "unit": "TFLOP/s", "frac": achieved / ffma_tf if ffma_tf else None,
+        "peak_source": "FP32 FFMA issue microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry); "
+                       f"nominal {FP32_NOMINAL_TFLOPS} TFLOP/s",
+        "frac_of_nominal": achieved / FP32_NOMINAL_TFLOPS,
+        "algorithmic_flops_per_launch": evals_checker * FLOPS_PER_EVAL, "avg_launch_ms": avg_ms, "launches_timed": chk_n,
+        "kernel_share_of_step": chk_ms / ms_local if ms_local else None,
+        "gevals_per_s": evals_checker / (avg_ms * 1e-3) / 1e9,
+        "tex_gsamples_per_s": evals_checker * 36 / (avg_ms * 1e-3) / 1e9, "tex_peak_gsamples_per_s": tex_g,
+        "tex_frac": (evals_checker * 36 / (avg_ms * 1e-3) / 1e9) / tex_g if tex_g else None,
+        "mufu_peak_gops_measured_lower_bound": mufu_g,
+        "hbm": {"bound": "hbm", "achieved": alg_bytes / (avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback"},
+        "traffic": traffic,
+    }
+    out = {
+        "metric": "depthmaps/s", "value": value, "unit": "depthmaps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "ours",
+        "config": {"workload": workload_name(args.config, cfg, iters), "timing": "inputs_larger_than_l2 (11 views x 25 MB + 0.4 GB state)"
+                   if args.config == "C2" else "see workload", "reference_views_per_gpu_per_step": 1, "parallelism": f"views sharded over {world} GPU(s)"},
+        "gevals_per_s": world * args.steps * n_evals / (ms * 1e-3) / 1e9, "evals_per_depthmap": n_evals,
+        "roofline": roofline, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_baseline(pkg, cfg, n_evals)
+        except Exception as e:  # the baseline must not take the bench down
+            out["cpu_baseline"] = {"error": repr(e)}
+    print(json.dumps(out))
+
+
+def run_reference(args):
+    """The reference's own kernels (oracle/_ref) on the same workload; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # the reference kernels printf debug lines ("after prop : ...", gipuma.cu:1043-1045): keep stdout for the JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+    import torch
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from oracle import ref_binding as rb
+    if not rb.available("asis"):
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libtsar_ref.so missing (run `make oracle` where the reference checkout exists)"})
+        return
+    torch.cuda.set_device(0)
+    cfg = pkg.scene.CONFIGS[args.config]
+    iters = 8
+    scene, imgs_dev, imgs_host, bgrx = build_scene(pkg, args.config, 0, "cuda:0")
+    from tsar_mvs_b200.engine import cameras_to_struct
+    cams = cameras_to_struct(scene["cams"])
+    params = pkg.make_params(box=11, iterations=iters, n_best=1, cost_comb=1, min_disparity=scene["min_disparity"],
+                             max_disparity=scene["max_disparity"])
+    ref = rb.RefEngine(pkg._lib.TsarCamera, pkg._lib.TsarParams, variant="asis")
+    ref.create([t.numpy() for t in imgs_host], cams, scene["subset"], params, scene["cam_f"])
+    ref.set_regions(scene["region_text"], scene["region_norm4"])
+    ref.upload(rb.F_CANNY, scene["canny"])
+
+    def step(seed):
+        rb.ref_slic(bgrx)
+        ref.init_planes(seed)
+        ref.iterate(iters, seed)
+        ref.lrdiff(); ref.getview()
+        ref.update_scale_2(); ref.update_scale(); ref.compute_disp()
+
+    for _ in range(args.warmup):
+        step(SEED)
+    torch.cuda.synchronize()
+    with ClockSampler(0) as clk:
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            step(SEED + 100 * k)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    value = args.steps / dt
+    # evaluation count by the same closed form
+    eng = pkg.DepthmapEngine(0)
+    eng.set_views_device([t.data_ptr() for t in imgs_dev], cfg["W"], cfg["H"], cams, scene["subset"], cam_f=scene["cam_f"])
+    eng.set_params(params)
+    n_evals = eng.eval_count(iters)
+    eng.close()
+    out = {
+        "metric": "depthmaps/s", "value": value, "unit": "depthmaps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": workload_name(args.config, cfg, iters), "note": "reference CUDA kernels rebuilt for sm_100a (gipuma.cu + gSLICr "
+                   "unmodified), managed memory, device sync after every kernel, warm (pages resident after warm-up); the reference has no CPU path"},
+        "gevals_per_s": args.steps * n_evals / dt / 1e9,
+        "cpu_baseline": {"value": value, "unit": "depthmaps/s", "cores": 0, "kind": "reference",
+                         "sample": f"{args.steps} full depthmaps of the workload on one B200 (the reference implements this path in CUDA only)"},
+        "e2e": {"value": value, "unit": "depthmaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "clocks": clk.summary(),
+    }
+    ref.close()
+    torch.cuda.synchronize()
+    emit(out)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -176,6 +176,10 @@ int tsar_launch_count(tsar_ctx *ctx, long long *count, int reset);
 /* pmCost evaluations (plane x source view x window) executed, from the closed form of
  * BASELINE.md section 3 evaluated with the exact border guards. */
 int tsar_eval_count(tsar_ctx *ctx, int iters, long long *n_evals);
+/* CUDA-event timing of the dominant kernel (the fused checkerboard propagation+refinement kernel) on the
+ * stream it is launched on: enable, run, then read the summed duration and the number of launches. */
+int tsar_profile(tsar_ctx *ctx, int enable);
+int tsar_profile_read(tsar_ctx *ctx, float *checker_ms_total, int *n_launches);
 const char *tsar_version(void);
 /* tex2D<float> of image `image` at n unnormalised coordinates (xy = n float2, host): used to
  * calibrate software models of the texture unit's bilinear filter. */

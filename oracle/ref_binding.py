@@ -119,3 +119,20 @@ class RefEngine:
         dt, _ = _DT.get(field, (np.float32, 1))
         arr = np.ascontiguousarray(arr, dt)
         self._ck(self.lib.ref_upload(self.h, field, arr.ctypes.data, arr.nbytes), "ref_upload")
+
+
+def ref_slic(bgrx, spixel_size=20, no_iters=5, coh_weight=5.0, enforce_connectivity=False):
+    """The reference's gSLICr GPU engine (gSLICr_seg_engine_GPU.cu unmodified) on a [h][w][4] uint8 image.
+    Returns (labels int32 [h][w], ms)."""
+    lib = C.CDLL(os.path.join(REF_DIR, "libgslic_ref.so"))
+    lib.ref_slic.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,
+                             C.POINTER(C.c_float)]
+    bgrx = np.ascontiguousarray(bgrx, np.uint8)
+    h, w = bgrx.shape[:2]
+    labels = np.empty((h, w), np.int32)
+    ms = C.c_float(0)
+    rc = lib.ref_slic(bgrx.ctypes.data, w, h, int(spixel_size), int(no_iters), float(coh_weight), int(enforce_connectivity),
+                      labels.ctypes.data, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"ref_slic failed ({rc})")
+    return labels, ms.value

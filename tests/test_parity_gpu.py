@@ -1,0 +1,241 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every product call goes through the C ABI
+(libtsar_b200.so); the checker is the reference's own gipuma.cu rebuilt for sm_100 (oracle/_ref):
+  * 'asis'     -- exactly as written (same-colour reads race, SURVEY Q3: not run-to-run reproducible);
+  * 'snapshot' -- 2-line build-time patch giving deterministic pre-launch-snapshot semantics.
+Bar: bit-exact against the snapshot build (integer/float bits identical); against the racy as-is build
+we report agreement next to the build's own run-to-run noise floor and require ours to be no further
+from it than the snapshot build is.
+"""
+import numpy as np
+import pytest
+
+from tests import parity_common as pc
+
+pytestmark = pytest.mark.gpu
+SEED = 20240601
+
+
+@pytest.fixture(scope="module")
+def env():
+    pkg = pc.load_pkg()
+    rb = pc.ref_binding()
+    if not rb.available("asis") or not rb.available("snapshot"):
+        pytest.fail("oracle/_ref/*.so missing: run `make oracle` where the reference checkout exists")
+    return pkg, rb
+
+
+@pytest.fixture(scope="module")
+def small(env):
+    pkg, _ = env
+    return pkg.scene.make_scene("small")
+
+
+@pytest.mark.parametrize("box,n_best,cost_comb", [(11, 1, 1), (11, 2, 1), (19, 1, 1), (7, 3, 1), (9, 2, 0)])
+def test_pmcost_multiview_bit_exact(env, small, box, n_best, cost_comb):
+    """pmCostMultiview_cu (gipuma.cu:456-518) on 50k random (pixel, plane) pairs incl. image borders."""
+    pkg, rb = env
+    params, mine, refs = pc.make_engines(pkg, small, box=box, n_best=n_best, cost_comb=cost_comb, variants=("asis",))
+    xy, planes = pc.random_planes(small, 50000)
+    c_m, b_m, r_m = mine.eval_planes(xy, planes, wrapper_rounding=True)
+    c_r, b_r, r_r = refs["asis"].eval_planes(xy, planes)
+    mine.close(); refs["asis"].close()
+    assert pc.frac_bit_exact(c_m, c_r) == 1.0
+    assert (b_m == b_r).all()
+    assert pc.frac_bit_exact(r_m, r_r) == 1.0
+
+
+def test_init_same_seed_bit_exact(env, small):
+    """gipuma_init_cu2 (gipuma.cu:679-729): same XORWOW streams, planes and costs from the reference's seed."""
+    pkg, rb = env
+    params, mine, refs = pc.make_engines(pkg, small, variants=("asis",))
+    mine.init_planes(SEED); refs["asis"].init_planes(SEED)
+    n_m, c_m = mine.download(pkg._lib.F_NORM4), mine.download(pkg._lib.F_COST)
+    n_r, c_r = refs["asis"].download(rb.F_NORM4), refs["asis"].download(rb.F_COST)
+    mine.close(); refs["asis"].close()
+    assert pc.frac_bit_exact(n_m, n_r) == 1.0
+    assert pc.frac_bit_exact(c_m, c_r) == 1.0
+    assert len(np.unique(n_m[..., 0])) > 1000  # really random
+
+
+def test_single_half_steps_bit_exact(env, small):
+    """Each checkerboard half-step from the reference's initial planes (tsar_load_planes)."""
+    pkg, rb = env
+    L = pkg._lib
+    params, mine, refs = pc.make_engines(pkg, small, variants=("asis", "snapshot"))
+    asis, snap = refs["asis"], refs["snapshot"]
+    asis.init_planes(SEED)
+    n0, c0 = asis.download(rb.F_NORM4), asis.download(rb.F_COST)
+    for kind in (L.BLACK_REFINE, L.RED_REFINE):  # refinement touches only the pixel itself: no race in the reference
+        asis.upload(rb.F_NORM4, n0); asis.upload(rb.F_COST, c0); asis.launch(kind, SEED + 1)
+        mine.load_planes(n0, c0); mine.launch(kind, SEED + 1)
+        assert pc.frac_bit_exact(mine.download(L.F_NORM4), asis.download(rb.F_NORM4)) == 1.0
+        assert pc.frac_bit_exact(mine.download(L.F_COST), asis.download(rb.F_COST)) == 1.0
+        assert (mine.download(L.F_BEVIEW) == asis.download(rb.F_BEVIEW)).all()
+        assert pc.frac_bit_exact(mine.download(L.F_RATIO), asis.download(rb.F_RATIO)) == 1.0
+    for kind in (L.BLACK_SPATIAL, L.RED_SPATIAL):
+        snap.upload(rb.F_NORM4, n0); snap.upload(rb.F_COST, c0); snap.launch(kind)
+        mine.load_planes(n0, c0); mine.launch(kind)
+        assert pc.frac_bit_exact(mine.download(L.F_NORM4), snap.download(rb.F_NORM4)) == 1.0
+        assert pc.frac_bit_exact(mine.download(L.F_COST), snap.download(rb.F_COST)) == 1.0
+        changed = 1.0 - pc.frac_bit_exact(mine.download(L.F_COST), c0)
+        assert changed > 0.2  # the step really propagated planes
+    for e in (mine, asis, snap):
+        e.close()
+
+
+@pytest.mark.parametrize("cfg,iters", [("small", 8), ("tiny", 3)])
+def test_full_sequence_vs_reference(env, cfg, iters):
+    """init -> iters x (bSP,bPR,rSP,rPR) -> getlrdiff -> getview -> compute_disp (gipuma.cu:1741-1761)."""
+    pkg, rb = env
+    L = pkg._lib
+    scene = pkg.scene.make_scene(cfg)
+    params, mine, refs = pc.make_engines(pkg, scene, iterations=iters, variants=("asis", "snapshot"))
+    asis, snap = refs["asis"], refs["snapshot"]
+    mine.depthmap(SEED)
+    o_m, conf_m = mine.download(L.F_NORM4), mine.download(L.F_CONFID)
+    snap.depthmap(SEED, iters=iters)
+    o_s, conf_s = snap.download(rb.F_NORM4), snap.download(rb.F_CONFID)
+    asis.depthmap(SEED, iters=iters); o_a = asis.download(rb.F_NORM4)
+    asis.depthmap(SEED, iters=iters); o_a2 = asis.download(rb.F_NORM4)
+    for e in (mine, asis, snap):
+        e.close()
+    # deterministic reference build: identical bits, so trivially inside the north-star tolerance
+    a = pc.output_agreement(o_m, o_s)
+    assert a["bit_exact"] == 1.0, a
+    assert a["frac_ok"] >= pc.GATE_FRACTION
+    assert pc.frac_bit_exact(conf_m, conf_s) == 1.0
+    # racy as-written build: we must be as close to it as its race-free twin is (its own noise floor is
+    # reported for the record and is below the 99 % gate on these scenes -- see DESIGN.md)
+    ours, twin, floor = pc.output_agreement(o_m, o_a), pc.output_agreement(o_s, o_a), pc.output_agreement(o_a2, o_a)
+    print(f"\n[{cfg}] ours-vs-asis {ours['frac_ok']:.4f} (depth {ours['frac_depth_ok']:.4f}), "
+          f"snapshot-vs-asis {twin['frac_ok']:.4f}, asis-vs-asis {floor['frac_ok']:.4f} (depth {floor['frac_depth_ok']:.4f})")
+    assert ours["frac_ok"] == twin["frac_ok"] and ours["frac_depth_ok"] == twin["frac_depth_ok"]
+
+
+def test_fused_equals_unfused(env, small, monkeypatch):
+    """Fusing spatial propagation + refinement of one colour into one kernel changes nothing."""
+    pkg, rb = env
+    params, fused, _ = pc.make_engines(pkg, small, iterations=3, variants=())
+    fused.depthmap(SEED)
+    o_f = fused.download(pkg._lib.F_NORM4)
+    monkeypatch.setenv("TSAR_B200_UNFUSED", "1")
+    params, unfused, _ = pc.make_engines(pkg, small, iterations=3, variants=())
+    unfused.depthmap(SEED)
+    o_u = unfused.download(pkg._lib.F_NORM4)
+    n_f, n_u = fused.launch_count(), unfused.launch_count()
+    fused.close(); unfused.close()
+    assert pc.frac_bit_exact(o_f, o_u) == 1.0
+    assert n_u > n_f > 0
+
+
+def test_run_is_deterministic(env, small):
+    pkg, rb = env
+    params, mine, _ = pc.make_engines(pkg, small, iterations=2, variants=())
+    mine.depthmap(SEED); a = mine.download(pkg._lib.F_NORM4)
+    mine.depthmap(SEED); b = mine.download(pkg._lib.F_NORM4)
+    mine.depthmap(SEED + 5); c = mine.download(pkg._lib.F_NORM4)
+    mine.close()
+    assert pc.frac_bit_exact(a, b) == 1.0
+    assert pc.frac_bit_exact(a, c) < 0.9  # a different seed gives different planes
+
+
+def test_glue_and_depth_completion_bit_exact(env, small):
+    """getlrdiff/getview/get_disp/update_scale(_2)/compute_disp (gipuma.cu:732-755, 810-844, 1161-1292)."""
+    pkg, rb = env
+    L = pkg._lib
+    scene = small
+    params, mine, refs = pc.make_engines(pkg, scene, variants=("snapshot",))
+    ref = refs["snapshot"]
+    ref.init_planes(SEED); ref.iterate(2, SEED)
+    n0, c0 = ref.download(rb.F_NORM4), ref.download(rb.F_COST)
+    mine.load_planes(n0, c0)
+    mine.upload(L.F_BEVIEW, ref.download(rb.F_BEVIEW)); mine.upload(L.F_RATIO, ref.download(rb.F_RATIO))
+    ref.lrdiff(); mine.lrdiff()
+    assert pc.frac_bit_exact(mine.download(L.F_LRDIFF), ref.download(rb.F_LRDIFF)) == 1.0
+    ref.getview(); mine.getview()
+    assert pc.frac_bit_exact(mine.download(L.F_CONFID), ref.download(rb.F_CONFID)) == 1.0
+    assert pc.frac_bit_exact(mine.download(L.F_DEPTH), ref.download(rb.F_DEPTH)) == 1.0
+    for e in (mine, ref):
+        e.set_regions(scene["region_text"], scene["region_norm4"])
+    mine.upload(L.F_CANNY, scene["canny"]); ref.upload(rb.F_CANNY, scene["canny"])
+    ref.update_scale_2(); mine.update_scale_2()
+    assert pc.frac_bit_exact(mine.download(L.F_FAKEDEPTH), ref.download(rb.F_FAKEDEPTH)) == 1.0
+    ref.update_scale(); mine.update_scale()
+    for fm, fr in ((L.F_NORM4, rb.F_NORM4), (L.F_COST, rb.F_COST), (L.F_SCALE, rb.F_SCALE), (L.F_DEPTH, rb.F_DEPTH)):
+        assert pc.frac_bit_exact(mine.download(fm), ref.download(fr)) == 1.0
+    filled = mine.download(L.F_SCALE)
+    assert 0.05 < filled.mean() < 0.5  # the textureless facet was completed
+    ref.compute_disp(); mine.compute_disp()
+    out = mine.download(L.F_NORM4)
+    assert pc.frac_bit_exact(out, ref.download(rb.F_NORM4)) == 1.0
+    # depth completion really put the region plane there: GT agreement inside the textureless facet
+    flat = scene["labels"] == 4
+    rel = np.abs(out[..., 3] - scene["gt_depth"]) / scene["gt_depth"]
+    assert np.median(rel[flat]) < 0.05
+    wn = out.copy()
+    dsp = np.where(wn[..., 3] > 0, scene["cam_f"] / np.maximum(wn[..., 3], 1e-6), 1.0).astype(np.float32)
+    for e, f_n, f_d in ((mine, L.F_NORM4, L.F_DEPTH), (ref, rb.F_NORM4, rb.F_DEPTH)):
+        e.upload(f_n, wn); e.upload(f_d, dsp)
+    ref.get_disp(); mine.get_disp()
+    assert pc.frac_bit_exact(mine.download(L.F_NORM4), ref.download(rb.F_NORM4)) == 1.0
+    mine.close(); ref.close()
+
+
+def test_edge_cases(env):
+    """Odd sizes (last row outside the reference's checkerboard grid), V = 1 and V = 2, tiny images."""
+    pkg, rb = env
+    L = pkg._lib
+    cfg = dict(W=67, H=33, n_images=3, V=2, fx=150.0, radius=1.0, arc_deg=14.0)
+    scene = pkg.scene.make_scene(cfg)
+    params, mine, refs = pc.make_engines(pkg, scene, iterations=2, variants=("snapshot",))
+    ref = refs["snapshot"]
+    mine.depthmap(SEED); ref.depthmap(SEED, iters=2)
+    assert pc.frac_bit_exact(mine.download(L.F_NORM4), ref.download(rb.F_NORM4)) == 1.0
+    mine.close(); ref.close()
+
+
+def test_host_entry_matches_resident_path(env, small):
+    """tsar_depthmap_host (host buffers in/out, the e2e path) == set_views + depthmap + download."""
+    pkg, rb = env
+    L = pkg._lib
+    params, mine, _ = pc.make_engines(pkg, small, iterations=2, variants=())
+    mine.depthmap(SEED)
+    a, ca = mine.download(L.F_NORM4), mine.download(L.F_CONFID)
+    e2 = pkg.DepthmapEngine(0)
+    b, cb = e2.depthmap_host(small["images"], small["cams"], small["subset"], params, SEED, cam_f=small["cam_f"])
+    mine.close(); e2.close()
+    assert pc.frac_bit_exact(a, b) == 1.0 and pc.frac_bit_exact(ca, cb) == 1.0
+
+
+def test_errors_are_codes_not_exits(env, small):
+    pkg, rb = env
+    e = pkg.DepthmapEngine(0)
+    with pytest.raises(pkg.TsarError):
+        e.init_planes(1)  # no views yet
+    with pytest.raises(pkg.TsarError):
+        e.set_views(small["images"], small["cams"], list(range(40)))  # V > 32
+    e.close()
+
+
+def test_smoke_entry(env):
+    import __graft_entry__ as g
+    g.smoke()
+
+
+@pytest.mark.parametrize("cfg,size,enforce", [("small", 20, False), ("small", 12, True), ("C1", 20, False)])
+def test_slic_labels_bit_exact(env, cfg, size, enforce):
+    """gSLICr (7 kernels, GPU.cu:213-379; settings of main.cpp:608-615): labels identical to the reference build,
+    including its as-compiled partial warp-tail reduction and window tiling (Q11)."""
+    pkg, rb = env
+    scene = pkg.scene.make_scene(cfg, with_colour=True)
+    bgrx = pkg.scene.box_downsample4(scene["bgr"]) if cfg == "C1" else np.concatenate(
+        [scene["bgr"], np.zeros(scene["bgr"].shape[:2] + (1,), np.uint8)], axis=-1)
+    eng = pkg.DepthmapEngine(0)
+    mine = eng.slic(bgrx, spixel_size=size, no_iters=5, coh_weight=5.0, enforce_connectivity=enforce)
+    ref, _ = rb.ref_slic(bgrx, spixel_size=size, no_iters=5, coh_weight=5.0, enforce_connectivity=enforce)
+    full = eng.slic(bgrx, spixel_size=size, correct_reduction=True)
+    eng.close()
+    assert mine.shape == ref.shape
+    assert (mine == ref).all(), f"{(mine != ref).mean():.4%} of labels differ"
+    assert len(np.unique(mine)) > 4
+    assert (full >= 0).all() and full.max() < (bgrx.shape[0] // size) * (bgrx.shape[1] // size)

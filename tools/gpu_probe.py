@@ -249,7 +249,26 @@ def s_time_c1():
     return r
 
 
-STAGES = dict(peaks=s_peaks, texcal=s_texcal, eval=s_eval, init=s_init, launch=s_launch, full=s_full, glue=s_glue,
+def s_slic():
+    res = {}
+    for cfg, size in (("small", 20), ("C1", 20)):
+        scene = pkg.scene.make_scene(cfg, with_colour=True)
+        bgrx = np.concatenate([scene["bgr"], np.zeros(scene["bgr"].shape[:2] + (1,), np.uint8)], axis=-1)
+        eng = pkg.DepthmapEngine(0)
+        for rep in range(2):
+            t = time.time(); mine = eng.slic(bgrx, spixel_size=size); t_m = time.time() - t
+        ref, ms_r = rb.ref_slic(bgrx, spixel_size=size)
+        ref, ms_r = rb.ref_slic(bgrx, spixel_size=size)
+        full = eng.slic(bgrx, spixel_size=size, correct_reduction=True)
+        res[cfg] = dict(labels_equal=float((mine == ref).mean()), n_labels=int(len(np.unique(ref))), wall_ms_mine=t_m * 1e3,
+                        ms_ref=ms_r, full_vs_parity=float((full == mine).mean()))
+        np.savez_compressed(os.path.join(OUT, f"slic_{cfg}.npz"), mine=mine, ref=ref, full=full)
+        log("[slic]", cfg, res[cfg])
+        eng.close()
+    return res
+
+
+STAGES = dict(slic=s_slic, peaks=s_peaks, texcal=s_texcal, eval=s_eval, init=s_init, launch=s_launch, full=s_full, glue=s_glue,
               time_c1=s_time_c1)
 
 if __name__ == "__main__":

@@ -66,6 +66,8 @@ struct tsar_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool fused = true;
     int eval_wrapper_rounding = 0;  // test-only, see tsar_dbg_eval_rounding
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // around every checkerboard kernel
     SlicState slic;
 };
 
@@ -187,13 +189,15 @@ static int ensure_state(tsar_ctx *ctx, size_t n) {
     return TSAR_OK;
 }
 
-// LineState::resize memsets every array to 0 (linestate.h:73-109)
-static int zero_state(tsar_ctx *ctx) {
+// LineState::resize memsets every array to 0 (linestate.h:73-109).  caller_inputs: also clear the arrays the
+// caller fills between the entry points (canny labels, reliable flags); a new view clears them, a re-run of
+// the PatchMatch path on the same view keeps them.
+static int zero_state(tsar_ctx *ctx, bool caller_inputs) {
     const size_t n = (size_t)ctx->W * ctx->H;
     cudaStream_t s = ctx->stream;
     for (int b = 0; b < 2; b++) { CK(cudaMemsetAsync(ctx->plane[b], 0, n * 16, s)); CK(cudaMemsetAsync(ctx->cost[b], 0, n * 4, s)); }
     CK(cudaMemsetAsync(ctx->depth, 0, n * 4, s)); CK(cudaMemsetAsync(ctx->fakedepth, 0, n * 4, s));
-    CK(cudaMemsetAsync(ctx->scale, 0, n * 4, s)); CK(cudaMemsetAsync(ctx->canny, 0, n * 4, s));
+    if (caller_inputs) { CK(cudaMemsetAsync(ctx->scale, 0, n * 4, s)); CK(cudaMemsetAsync(ctx->canny, 0, n * 4, s)); }
     CK(cudaMemsetAsync(ctx->ratio, 0, n * 4, s)); CK(cudaMemsetAsync(ctx->lrdiff, 0, n * 4, s));
     CK(cudaMemsetAsync(ctx->confid, 0, n * 4, s)); CK(cudaMemsetAsync(ctx->beview, 0, n * 4, s));
     ctx->cur[0] = ctx->cur[1] = 0;
@@ -247,7 +251,16 @@ static int launch_checker(tsar_ctx *ctx, int mode, int colour) {
     a.beview = ctx->beview;
     a.rng = ctx->rng;
     a.colour = colour;
+    cudaEvent_t p0 = nullptr, p1 = nullptr;
+    if (ctx->profiling) {
+        CK(cudaEventCreate(&p0)); CK(cudaEventCreate(&p1));
+        CK(cudaEventRecord(p0, ctx->stream));
+    }
     CK(ctx->variant->checker(mode, ctx->pm, ctx->ref_img, a, ctx->stream));
+    if (ctx->profiling) {
+        CK(cudaEventRecord(p1, ctx->stream));
+        ctx->prof_events.emplace_back(p0, p1);
+    }
     ctx->launches++;
     ctx->cur[colour] = out;
     return TSAR_OK;
@@ -393,7 +406,7 @@ int tsar_set_views(tsar_ctx *ctx, int W, int H, int n_images, const float *const
     }
     ctx->have_views = true;
     ctx->have_planes = false;
-    rc = zero_state(ctx);
+    rc = zero_state(ctx, true);
     if (rc) return rc;
     return rebuild_constants(ctx);
 }
@@ -410,7 +423,7 @@ int tsar_set_params(tsar_ctx *ctx, const tsar_params *p) {
 int tsar_init_planes(tsar_ctx *ctx, uint64_t seed) {
     int rc = need_ready(ctx);
     if (rc) return rc;
-    if ((rc = zero_state(ctx))) return rc;
+    if ((rc = zero_state(ctx, false))) return rc;
     if ((rc = make_rng_table(ctx, seed))) return rc;
     CK(ctx->variant_init->init(ctx->pm_init, ctx->ref_img, ctx->rng, ctx->rng_len, ctx->plane[0], ctx->cost[0], ctx->stream));
     ctx->launches++;
@@ -754,6 +767,28 @@ int tsar_dbg_tex_sample(tsar_ctx *ctx, int image, int n, const float *xy, float 
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return TSAR_OK;
+}
+
+int tsar_profile(tsar_ctx *ctx, int enable) {
+    if (!ctx) return TSAR_ERR_ARG;
+    ctx->profiling = enable != 0;
+    return TSAR_OK;
+}
+
+int tsar_profile_read(tsar_ctx *ctx, float *checker_ms_total, int *n_launches) {
+    if (!ctx || !checker_ms_total || !n_launches) return TSAR_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    float tot = 0.f;
+    for (auto &pr : ctx->prof_events) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        tot += ms;
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    *checker_ms_total = tot;
+    *n_launches = (int)ctx->prof_events.size();
+    ctx->prof_events.clear();
     return TSAR_OK;
 }
 

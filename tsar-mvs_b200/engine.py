@@ -197,6 +197,21 @@ class DepthmapEngine:
         self._ck(self.lib.tsar_eval_count(self.h, int(iters), C.byref(n)), "tsar_eval_count")
         return n.value
 
+    def profile(self, enable=True):
+        self._ck(self.lib.tsar_profile(self.h, int(enable)), "tsar_profile")
+
+    def profile_read(self):
+        """(summed CUDA-event ms of the checkerboard kernels, number of launches) since profiling was enabled."""
+        ms, n = C.c_float(0), C.c_int(0)
+        self._ck(self.lib.tsar_profile_read(self.h, C.byref(ms), C.byref(n)), "tsar_profile_read")
+        return ms.value, n.value
+
+    def peaks(self):
+        """Issue-rate microbenchmarks: (FP32 FFMA TFLOP/s, MUFU Gop/s, bilinear texture Gsamples/s)."""
+        out = (C.c_float * 3)()
+        self._ck(self.lib.tsar_dbg_peaks(self.h, out), "tsar_dbg_peaks")
+        return out[0], out[1], out[2]
+
     # -- gSLICr ------------------------------------------------------------------------------------
     def slic(self, bgrx, spixel_size=20, no_iters=5, coh_weight=5.0, enforce_connectivity=False,
              correct_reduction=False):

@@ -31,8 +31,9 @@ def _look_at(C, target):
     return np.stack([x, y, z])  # rows: world -> camera
 
 
-def make_cameras(W, H, n_images, fx, radius, arc_deg, depth_range=(0.7, 1.45), order="nearest"):
-    """Camera 0 is the reference; the others sit on an arc around it, sorted by baseline."""
+def make_cameras(W, H, n_images, fx, radius, arc_deg, depth_range=(0.7, 1.45), ref_index=0):
+    """Cameras on an arc, sorted by baseline from the middle one.  Camera `ref_index` of that list becomes
+    the reference (index 0 of the returned list); the others keep their order."""
     K = np.array([[fx, 0, (W - 1) / 2.0], [0, fx, (H - 1) / 2.0], [0, 0, 1.0]])
     target = np.zeros(3)
     half = np.deg2rad(arc_deg) / 2.0
@@ -51,6 +52,8 @@ def make_cameras(W, H, n_images, fx, radius, arc_deg, depth_range=(0.7, 1.45), o
         Rs.append(R)
         Cs.append(C)
         ts.append(-R @ C)
+    order = [ref_index % n_images] + [i for i in range(n_images) if i != ref_index % n_images]
+    Rs, ts, Cs = [Rs[i] for i in order], [ts[i] for i in order], [Cs[i] for i in order]
     R0, t0 = Rs[0], ts[0]
     cams = []
     for i in range(n_images):
@@ -133,6 +136,48 @@ class Scene:
         img = np.rint(self.intensity(X, textured)).astype(np.uint8)
         return img, best_t, label
 
+    def render_torch(self, cam, W, H, device):
+        """Same renderer with torch (float64) so large bench scenes are rendered on the GPU in < 1 s.
+        sin() may differ from numpy in the last bit, i.e. +-1 grey level in rare pixels: fine for the
+        benchmark (both arms get the same images); parity fixtures always use the numpy path."""
+        import torch
+        dt = torch.float64
+        tt = lambda a: torch.as_tensor(np.asarray(a, float), dtype=dt, device=device)
+        R, C, Kinv = tt(cam["_R_world"]), tt(cam["_C_world"]), tt(cam["K_inv"])
+        img = torch.empty((H, W), dtype=torch.float32, device=device)
+        depth = torch.empty((H, W), dtype=torch.float32, device=device)
+        label = torch.empty((H, W), dtype=torch.int32, device=device)
+        omega, phase, amp, fomega = tt(self.omega), tt(self.phase), tt(self.amp), tt(self.flat_omega)
+        step = max(1, (1 << 22) // W)
+        xs = torch.arange(W, dtype=dt, device=device)
+        for r0 in range(0, H, step):
+            r1 = min(H, r0 + step)
+            ys = torch.arange(r0, r1, dtype=dt, device=device)
+            yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+            d_cam = torch.stack([Kinv[0, 0] * xx + Kinv[0, 2], Kinv[1, 1] * yy + Kinv[1, 2], torch.ones_like(xx)], dim=-1)
+            d = d_cam @ R
+            best_t = torch.full(xx.shape, float("inf"), dtype=dt, device=device)
+            lab = torch.zeros(xx.shape, dtype=torch.int32, device=device)
+            for idx, f in enumerate(self.facets):
+                n, p0 = tt(f["n"]), tt(f["p0"])
+                t = (n @ (p0 - C)) / (d @ n)
+                rel = C + t[..., None] * d - p0
+                ok = (t > 0) & torch.isfinite(t)
+                if np.isfinite(f["hu"]):
+                    ok &= ((rel @ tt(f["u"])).abs() <= f["hu"]) & ((rel @ tt(f["v"])).abs() <= f["hv"])
+                upd = ok & (t < best_t)
+                best_t = torch.where(upd, t, best_t)
+                lab = torch.where(upd, torch.full_like(lab, idx), lab)
+            X = C + best_t[..., None] * d
+            textured = torch.as_tensor([f["textured"] for f in self.facets], device=device)[lab.long()]
+            val = 127.5 + torch.sin(X @ omega.T + phase) @ amp
+            flat = 128.0 + (torch.sin(X @ fomega) > 0.3).to(dt)
+            v = torch.where(textured, val.clamp(0, 255), flat)
+            img[r0:r1] = torch.round(v).to(torch.float32)
+            depth[r0:r1] = best_t.to(torch.float32)
+            label[r0:r1] = lab
+        return img, depth, label
+
     def region_planes(self, cam0, perturb=0.0):
         """Per-facet plane (n, d) with n.X + d = 0 in the reference camera frame (linestate.h:12)."""
         R, C = cam0["_R_world"], cam0["_C_world"]
@@ -147,16 +192,28 @@ class Scene:
         return np.array(out)
 
 
-def make_scene(name_or_cfg, seed=1234, with_colour=False):
+def reorder_reference(cams_world, ref_index):
+    """Camera list with camera `ref_index` moved to the front (it becomes the reference view)."""
+    order = [ref_index] + [i for i in range(len(cams_world)) if i != ref_index]
+    return order
+
+
+def make_scene(name_or_cfg, seed=1234, with_colour=False, ref_index=0, backend="numpy", device=None):
     """Builds a full test case: images (float32 0..255, image 0 = reference), cameras, view subset,
     algorithm parameters, ground-truth depth / facet labels of the reference view, region table."""
     cfg = CONFIGS[name_or_cfg] if isinstance(name_or_cfg, str) else dict(name_or_cfg)
     W, H, n, V = cfg["W"], cfg["H"], cfg["n_images"], cfg["V"]
-    cams = make_cameras(W, H, n, cfg["fx"], cfg["radius"], cfg["arc_deg"])
+    cams = make_cameras(W, H, n, cfg["fx"], cfg["radius"], cfg["arc_deg"], ref_index=ref_index)
     sc = Scene(W, H, cfg["fx"], cfg["radius"], seed=seed)
     images = []
     gt_depth = labels = None
     for i, cam in enumerate(cams):
+        if backend == "torch":
+            im, dep, lab = sc.render_torch(cam, W, H, device)
+            images.append(im)  # stays a torch tensor (on `device`)
+            if i == 0:
+                gt_depth, labels = dep.cpu().numpy(), lab.cpu().numpy()
+            continue
         parts = []
         step = max(1, (1 << 21) // W)  # render in row bands to bound memory
         for r0 in range(0, H, step):
@@ -177,7 +234,7 @@ def make_scene(name_or_cfg, seed=1234, with_colour=False):
                min_disparity=min_disp, max_disparity=max_disp, gt_depth=gt_depth, labels=labels,
                region_text=text, region_norm4=planes, canny=labels.astype(np.float32))
     if with_colour:
-        ref = images[0]
+        ref = images[0] if backend == "numpy" else images[0].cpu().numpy()
         g = np.roll(ref, 3, axis=1)
         r = np.roll(ref, 5, axis=0)
         out["bgr"] = np.stack([ref, g, r], axis=-1).astype(np.uint8)
