@@ -8,7 +8,7 @@ NVFLAGS   := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Iinclude
 PKG       := tsar-mvs_b200
 SRC       := $(PKG)/csrc
 BUILD     := build/obj
-OBJS      := $(BUILD)/context.o $(BUILD)/pm_inst_w11.o $(BUILD)/pm_inst_w19.o $(BUILD)/pm_inst_generic.o \
+OBJS      := $(BUILD)/context.o $(BUILD)/pm_inst_w11.o $(BUILD)/pm_inst_w11b.o $(BUILD)/pm_inst_w11c.o $(BUILD)/pm_inst_w11d.o $(BUILD)/pm_inst_w11e.o $(BUILD)/pm_inst_w11f.o $(BUILD)/pm_inst_w19.o $(BUILD)/pm_inst_generic.o \
              $(BUILD)/pm_misc.o
 HDRS      := $(wildcard $(SRC)/*.cuh $(SRC)/*.h $(SRC)/*.inc include/*.h)
 

@@ -71,9 +71,11 @@ __global__ void ref_eval_kernel(GlobalState &gs, int n, const int2 *xy, const fl
 }
 
 #ifdef ORACLE_SNAPSHOT
-__global__ void ref_merge_colour(GlobalState &gs, int colour) {
+// y_limit: rows reached by the reference's checkerboard grid (gipuma.cu:1721; for some odd heights the last
+// row is never processed, so there is nothing to merge there)
+__global__ void ref_merge_colour(GlobalState &gs, int colour, int y_limit) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= gs.cameras->cols || y >= gs.cameras->rows) return;
+    if (x >= gs.cameras->cols || y >= gs.cameras->rows || y >= y_limit) return;
     if (((x + y) & 1) != colour) return;
     int p = y * gs.cameras->cols + x;
     gs.lines->c[p] = gs.lines->ransa[p];
@@ -282,7 +284,7 @@ static int launch_kind(RefCtx *r, int kind, uint64_t seed, bool sync) {
         case TSAR_BLACK_SPATIAL:
             gipuma_black_spatialProp_cu<float><<<r->grid_cb, r->block_cb>>>(gs, false);
 #ifdef ORACLE_SNAPSHOT
-            ref_merge_colour<<<r->grid_px, r->block_px>>>(gs, 0);
+            ref_merge_colour<<<r->grid_px, r->block_px>>>(gs, 0, 32 * (int)r->grid_cb.y);
 #endif
             break;
         case TSAR_BLACK_REFINE:
@@ -292,7 +294,7 @@ static int launch_kind(RefCtx *r, int kind, uint64_t seed, bool sync) {
         case TSAR_RED_SPATIAL:
             gipuma_red_spatialProp_cu<float><<<r->grid_cb, r->block_cb>>>(gs, false);
 #ifdef ORACLE_SNAPSHOT
-            ref_merge_colour<<<r->grid_px, r->block_px>>>(gs, 1);
+            ref_merge_colour<<<r->grid_px, r->block_px>>>(gs, 1, 32 * (int)r->grid_cb.y);
 #endif
             break;
         case TSAR_RED_REFINE:

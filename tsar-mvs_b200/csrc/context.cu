@@ -99,7 +99,15 @@ static const PmVariant *pick_variant(const tsar_params &p, bool init) {
     const int hs = p.box_hsize, vs = p.box_vsize;
     const int hr = init ? hs / 2 : (hs - 1) / 2, vr = init ? vs / 2 : (vs - 1) / 2;
     const bool fast_comb = (p.cost_comb == 1 && p.n_best <= 2);
-    if (fast_comb && hr == vr && hr == 5) return &pm_variant_w11;
+    if (fast_comb && hr == vr && hr == 5) {
+        const char *v = getenv("TSAR_B200_W11_VARIANT");  // launch-shape experiments; results are identical
+        if (v && v[0] == 'b') return &pm_variant_w11b;
+        if (v && v[0] == 'c') return &pm_variant_w11c;
+        if (v && v[0] == 'd') return &pm_variant_w11d;
+        if (v && v[0] == 'e') return &pm_variant_w11e;
+        if (v && v[0] == 'f') return &pm_variant_w11f;
+        return &pm_variant_w11;
+    }
     if (fast_comb && hr == vr && hr == 9) return &pm_variant_w19;
     return &pm_variant_generic;
 }

@@ -20,6 +20,17 @@
 
 #include "pm_math.cuh"
 
+// outer-loop unroll of the branch-free sampling loop (window columns per trip); a translation unit may
+// override it before including this header
+#ifndef PM_FAST_UNROLL
+#define PM_FAST_UNROLL(n1) (((n1) + 1) / 2)
+#endif
+
+// columns of the checkerboard tile covered by one warp (32 = the reference's mapping)
+#ifndef PM_WARP_COLS
+#define PM_WARP_COLS 32
+#endif
+
 namespace tsar {
 
 constexpr int kMaxViews = 32;
@@ -79,10 +90,11 @@ __device__ __forceinline__ RefStats window_weights(const PmConst &c, const float
     const int n1x = N1 ? N1 : c.n1x, n1y = N1 ? N1 : c.n1y;
     const int hrad = N1 ? N1 - 1 : c.hrad, vrad = N1 ? N1 - 1 : c.vrad;
     int k = 0;
-#pragma unroll
+    // runs once per pixel per launch: kept rolled (code size matters more than its speed)
+#pragma unroll 1
     for (int ii = 0; ii < n1x; ii++) {
         const int xi = min(max(x - hrad + 2 * ii, 0), W - 1);
-#pragma unroll
+#pragma unroll 2
         for (int jj = 0; jj < n1y; jj++, k++) {
             const int yj = min(max(y - vrad + 2 * jj, 0), H - 1);
             const float r = __ldg(ref + (size_t)yj * W + xi);
@@ -173,8 +185,11 @@ __device__ __forceinline__ float view_cost(const PmConst &c, int vi, int x, int 
     const bool fast = (zmin >= kDivLo) && (zmin >= 9.765625e-4f * zs) && (zs <= kDivHi) && (xs <= kDivHi) && (ys <= kDivHi);
 
     int k = 0;
+    constexpr int kUnr = N1 ? PM_FAST_UNROLL(N1) : 1;
     if (fast) {
-#pragma unroll
+        // half of the window per trip when the size is known: enough independent texture fetches in flight
+        // to cover their latency, small enough to stay in the instruction cache
+#pragma unroll(kUnr)
         for (int ii = 0; ii < n1x; ii++) {
             const float px = (float)(x - hrad + 2 * ii);
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;

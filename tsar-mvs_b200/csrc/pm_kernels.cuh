@@ -90,8 +90,17 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
     fill_spatial_table<N1>(c, sm.sp, tid, NT);
     __syncthreads();
     const int W = c.W, H = c.H;
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = (blockIdx.y * (NT / 32) + threadIdx.y) * 2 + ((x + a.colour) & 1);
+    // Pixel of this thread inside the CTA's tile of 32 columns x 2*(NT/32) rows.  The reference maps a warp
+    // to 32 consecutive columns of one row pair (gipuma.cu:1099-1103); which thread takes which pixel does
+    // not change any result (pixels of one colour are independent), but a more compact warp footprint
+    // (PM_WARP_COLS = 16 or 8 columns x 2 or 4 row pairs) lowers the number of texture-cache wavefronts
+    // each warp-wide fetch needs.
+    constexpr int WC = PM_WARP_COLS;          // columns per warp: 32, 16 or 8
+    constexpr int WPR = 32 / WC;              // warps side by side in the 32-column tile
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int x = blockIdx.x * 32 + (warp % WPR) * WC + (lane % WC);
+    const int rowpair = (warp / WPR) * (32 / WC) + (lane / WC);
+    const int y = (blockIdx.y * (NT / 32) + rowpair) * 2 + ((x + a.colour) & 1);
     if (x >= W || y >= H || y >= c.y_limit) return;
     const int own = a.colour;
     const int pidx = y * W + x;
@@ -110,113 +119,126 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
     int beview_now = 0;
     bool meta_dirty = false;
 
-    if (DO_SP) {
-        // evaluate the plane of neighbour `pt` at this pixel (spatialPropagation_cu, gipuma.cu:525-566)
-        auto try_plane = [&](int pt, bool from_own) {
-            const float4 cand = from_own ? pS[pt] : pO[pt];
-            const float dep = plane_depth(c, cand, x, y);
-            if (dep >= c.depthMin && dep <= c.depthMax) {  // the cost has no side effect: skip it when the
-                                                           // depth test would reject the plane anyway
-                const MvResult r = multiview_cost<NT, N1, GEN>(c, x, y, cand, wt, rs);
-                if (r.cost < cost_now) {
-                    cost_now = r.cost; norm_now = cand; ratio_now = r.ratio; beview_now = r.beview;
-                    meta_dirty = true;
-                }
-            }
-        };
-        float cmin;
-        int best;
-        // -- four far strips: 11 samples, stride 2, all of the opposite colour (gipuma.cu:888-950)
-        if (y > 2) {  // up_far
-            best = pidx - 3 * W; cmin = cO[best];
-#pragma unroll
-            for (int i = 1; i < 11; i++)
-                if (y > 2 + 2 * i) { const int pt = pidx - (3 + 2 * i) * W; const float v = cO[pt]; if (v < cmin) { cmin = v; best = pt; } }
-            try_plane(best, false);
-        }
-        if (y < H - 3) {  // down_far: the running minimum starts from c[up_far]; that index is
-                          // out of bounds for y < 3 and reads the zero guard (Q5)
-            cmin = (y >= 3) ? cO[pidx - 3 * W] : 0.0f;
-            best = pidx + 3 * W;
-#pragma unroll
-            for (int i = 1; i < 11; i++)
-                if (y < H - 3 - 2 * i) { const int pt = pidx + (3 + 2 * i) * W; const float v = cO[pt]; if (v < cmin) { cmin = v; best = pt; } }
-            try_plane(best, false);
-        }
-        if (x > 2) {  // left_far
-            best = pidx - 3; cmin = cO[best];
-#pragma unroll
-            for (int i = 1; i < 11; i++)
-                if (x > 2 + 2 * i) { const int pt = pidx - 3 - 2 * i; const float v = cO[pt]; if (v < cmin) { cmin = v; best = pt; } }
-            try_plane(best, false);
-        }
-        if (x < W - 3) {  // right_far: comparison is inverted in the reference (tracks the maximum, Q6)
-            best = pidx + 3; cmin = cO[best];
-#pragma unroll
-            for (int i = 1; i < 11; i++)
-                if (x < W - 3 - 2 * i) { const int pt = pidx + 3 + 2 * i; const float v = cO[pt]; if (cmin < v) { cmin = v; best = pt; } }
-            try_plane(best, false);
-        }
-        // -- four near "V" areas: the direct neighbour (opposite colour) plus same-colour extras
-        //    (gipuma.cu:952-1042); same-colour values come from the pre-launch snapshot
-        bool bown;
-        if (y > 0) {  // up_near
-            best = pidx - W; cmin = cO[best]; bown = false;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                if (y > 1 + i && x > i) { const int pt = pidx - (2 + i) * W - i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-                if (y > 1 + i && x < W - 1 - i) { const int pt = pidx - (2 + i) * W + i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-            }
-            try_plane(best, bown);
-        }
-        if (y < H - 1) {  // down_near
-            best = pidx + W; cmin = cO[best]; bown = false;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                if (y < H - 2 - i && x > i) { const int pt = pidx + (2 + i) * W - i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-                if (y < H - 2 - i && x < W - 1 - i) { const int pt = pidx + (2 + i) * W + i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-            }
-            try_plane(best, bown);
-        }
-        if (x > 0) {  // left_near
-            best = pidx - 1; cmin = cO[best]; bown = false;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                if (x > 1 + i && y > i) { const int pt = pidx - (2 + i) - i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-                if (x > 1 + i && y < H - 1 - i) { const int pt = pidx - (2 + i) + i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-            }
-            try_plane(best, bown);
-        }
-        if (x < W - 1) {  // right_near
-            best = pidx + 1; cmin = cO[best]; bown = false;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                if (x < W - 2 - i && y > i) { const int pt = pidx + (2 + i) - i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-                if (x < W - 2 - i && y < H - 1 - i) { const int pt = pidx + (2 + i) + i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-            }
-            try_plane(best, bown);
-        }
-    }
+    // refinement state (planeRefinement_cu + getRndDispAndUnitVector_cu, gipuma.cu:582-676)
+    float vx = 0.f, vy = 0.f, vz = 0.f, depth_now = 0.f, deltaN = 1.0f, deltaZ = fmul(c.max_disp, 0.5f);
+    const uint32_t *row = a.rng + (size_t)y * c.rng_pitch + x;
+    const float fb = fmul(c.baseline, c.f_params);
+    int draw = 0;
 
-    if (DO_PR) {
-        // planeRefinement_cu + getRndDispAndUnitVector_cu (gipuma.cu:582-676)
-        float vx, vy, vz;
-        view_vector(c, x, y, vx, vy, vz);
-        float depth_now = plane_depth(c, norm_now, x, y);  // gipuma.cu:1073
-        const uint32_t *row = a.rng + (size_t)y * c.rng_pitch + x;
-        const float fb = fmul(c.baseline, c.f_params);
-        float deltaN = 1.0f;
-        int n = 0;
-        for (float deltaZ = fmul(c.max_disp, 0.5f); deltaZ >= 0.01f; deltaZ = fdiv(deltaZ, 10.0f)) {
-            const float u0 = uniform01(row[n]), u1 = uniform01(row[n + 1]), u2 = uniform01(row[n + 2]),
-                        u3 = uniform01(row[n + 3]);
-            n += 4;
+    // ONE hypothesis loop with ONE call site of the cost function: steps 0..7 are the eight propagation
+    // candidates (gipuma.cu:888-1042, in the reference's order), steps >= 8 the refinement rounds.  Keeping a
+    // single copy of the (large, unrolled) cost code is what keeps the kernel inside the instruction cache.
+#pragma unroll 1
+    for (int step = DO_SP ? 0 : 8;; step++) {
+        float4 cand;
+        float cand_depth = 0.f;
+        bool eval = false;
+        if (step < 8) {
+            // -- pick the neighbour whose plane is tried at this pixel
+            float cmin;
+            int best = -1;
+            bool bown = false;
+            switch (step) {
+                case 0:  // up_far: 11 samples, stride 2, opposite colour
+                    if (y > 2) {
+                        best = pidx - 3 * W; cmin = cO[best];
+#pragma unroll
+                        for (int i = 1; i < 11; i++)
+                            if (y > 2 + 2 * i) { const int pt = pidx - (3 + 2 * i) * W; const float v = cO[pt]; if (v < cmin) { cmin = v; best = pt; } }
+                    }
+                    break;
+                case 1:  // down_far: the running minimum starts from c[up_far]; out of bounds for
+                         // y < 3, where the reference reads the zero guard (Q5)
+                    if (y < H - 3) {
+                        cmin = (y >= 3) ? cO[pidx - 3 * W] : 0.0f;
+                        best = pidx + 3 * W;
+#pragma unroll
+                        for (int i = 1; i < 11; i++)
+                            if (y < H - 3 - 2 * i) { const int pt = pidx + (3 + 2 * i) * W; const float v = cO[pt]; if (v < cmin) { cmin = v; best = pt; } }
+                    }
+                    break;
+                case 2:  // left_far
+                    if (x > 2) {
+                        best = pidx - 3; cmin = cO[best];
+#pragma unroll
+                        for (int i = 1; i < 11; i++)
+                            if (x > 2 + 2 * i) { const int pt = pidx - 3 - 2 * i; const float v = cO[pt]; if (v < cmin) { cmin = v; best = pt; } }
+                    }
+                    break;
+                case 3:  // right_far: comparison inverted in the reference (tracks the maximum, Q6)
+                    if (x < W - 3) {
+                        best = pidx + 3; cmin = cO[best];
+#pragma unroll
+                        for (int i = 1; i < 11; i++)
+                            if (x < W - 3 - 2 * i) { const int pt = pidx + 3 + 2 * i; const float v = cO[pt]; if (cmin < v) { cmin = v; best = pt; } }
+                    }
+                    break;
+                // near "V" areas: the direct neighbour (opposite colour) + same-colour extras, which are read
+                // from the pre-launch snapshot (gipuma.cu:952-1042)
+                case 4:  // up_near
+                    if (y > 0) {
+                        best = pidx - W; cmin = cO[best];
+#pragma unroll
+                        for (int i = 0; i < 3; i++) {
+                            if (y > 1 + i && x > i) { const int pt = pidx - (2 + i) * W - i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+                            if (y > 1 + i && x < W - 1 - i) { const int pt = pidx - (2 + i) * W + i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+                        }
+                    }
+                    break;
+                case 5:  // down_near
+                    if (y < H - 1) {
+                        best = pidx + W; cmin = cO[best];
+#pragma unroll
+                        for (int i = 0; i < 3; i++) {
+                            if (y < H - 2 - i && x > i) { const int pt = pidx + (2 + i) * W - i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+                            if (y < H - 2 - i && x < W - 1 - i) { const int pt = pidx + (2 + i) * W + i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+                        }
+                    }
+                    break;
+                case 6:  // left_near
+                    if (x > 0) {
+                        best = pidx - 1; cmin = cO[best];
+#pragma unroll
+                        for (int i = 0; i < 3; i++) {
+                            if (x > 1 + i && y > i) { const int pt = pidx - (2 + i) - i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+                            if (x > 1 + i && y < H - 1 - i) { const int pt = pidx - (2 + i) + i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+                        }
+                    }
+                    break;
+                default:  // 7: right_near
+                    if (x < W - 1) {
+                        best = pidx + 1; cmin = cO[best];
+#pragma unroll
+                        for (int i = 0; i < 3; i++) {
+                            if (x < W - 2 - i && y > i) { const int pt = pidx + (2 + i) - i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+                            if (x < W - 2 - i && y < H - 1 - i) { const int pt = pidx + (2 + i) + i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
+                        }
+                    }
+                    break;
+            }
+            if (best >= 0) {
+                // spatialPropagation_cu (gipuma.cu:525-566).  The cost has no side effect, so it is skipped when
+                // the depth-range test would reject the plane anyway.
+                cand = bown ? pS[best] : pO[best];
+                const float dep = plane_depth(c, cand, x, y);
+                eval = (dep >= c.depthMin && dep <= c.depthMax);
+            }
+        } else {
+            if (!DO_PR) break;
+            if (step == 8) {
+                view_vector(c, x, y, vx, vy, vz);
+                depth_now = plane_depth(c, norm_now, x, y);  // gipuma.cu:1073
+            }
+            if (!(deltaZ >= 0.01f)) break;                   // for (deltaZ = max/2; deltaZ >= 0.01; deltaZ /= 10)
+            const float u0 = uniform01(row[draw]), u1 = uniform01(row[draw + 1]), u2 = uniform01(row[draw + 2]),
+                        u3 = uniform01(row[draw + 3]);
+            draw += 4;
             const float disp = fdiv(fb, depth_now);                          // :596
             const float lo = fminf(fadd(c.min_disp, disp), deltaZ);          // = -minDelta, :601
             const float hi = fminf(fsub(c.max_disp, disp), deltaZ);          // = maxDelta,  :602
-            float nd = fadd(ffma(u0, fadd(lo, hi), -lo), disp);              // disp + between(minDelta,maxDelta)
+            float nd = fadd(ffma(u0, fadd(lo, hi), -lo), disp);              // disp + between(minDelta, maxDelta)
             nd = fminf(c.max_disp, fmaxf(c.min_disp, nd));                   // :608
-            const float depth = fdiv(fb, nd);                                // :610
+            cand_depth = fdiv(fb, nd);                                       // :610
             const float two = fadd(deltaN, deltaN);
             float nx = fadd(norm_now.x, ffma(two, u1, -deltaN));             // :613-615
             float ny = fadd(norm_now.y, ffma(two, u2, -deltaN));
@@ -224,14 +246,17 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
             const float rn = rsqrtf(dot3(nx, nx, ny, ny, nz, nz));           // normalize_cu
             nx = fmul(nx, rn); ny = fmul(ny, rn); nz = fmul(nz, rn);
             if (dot3(vx, nx, vy, ny, vz, nz) > 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
-            float4 cand = make_float4(nx, ny, nz, 0.f);
-            cand.w = plane_d(c, nx, ny, nz, x, y, depth);                    // :654
-            const MvResult r = multiview_cost<NT, N1, GEN>(c, x, y, cand, wt, rs);
-            if (r.cost < cost_now) {                                         // :665 (no depth-range test)
-                cost_now = r.cost; norm_now = cand; depth_now = depth; ratio_now = r.ratio; beview_now = r.beview;
-                meta_dirty = true;
-            }
+            cand = make_float4(nx, ny, nz, plane_d(c, nx, ny, nz, x, y, cand_depth));   // :654
+            eval = true;                                                     // no depth-range test (:665)
+            deltaZ = fdiv(deltaZ, 10.0f);
             deltaN = fmul(deltaN, 0.25f);
+        }
+        if (eval) {
+            const MvResult r = multiview_cost<NT, N1, GEN>(c, x, y, cand, wt, rs);
+            if (r.cost < cost_now) {
+                cost_now = r.cost; norm_now = cand; ratio_now = r.ratio; beview_now = r.beview; meta_dirty = true;
+                depth_now = cand_depth;  // only read by the refinement rounds
+            }
         }
     }
 

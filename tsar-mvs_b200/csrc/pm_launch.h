@@ -32,6 +32,7 @@ struct PmVariant {
 };
 
 extern const PmVariant pm_variant_w11;      // 11x11 window (hRad 5, 36 samples), n_best <= 2 / COMB_BEST_N
+extern const PmVariant pm_variant_w11b, pm_variant_w11c, pm_variant_w11d, pm_variant_w11e, pm_variant_w11f;  // experimental launch shapes (env TSAR_B200_W11_VARIANT)
 extern const PmVariant pm_variant_w19;      // 19x19 window (hRad 9, 100 samples), n_best <= 2 / COMB_BEST_N
 extern const PmVariant pm_variant_generic;  // any window, any combination (run-time loops)
 

@@ -1,0 +1,31 @@
+"""Sharding of reference views over GPUs.  Reference views are independent units (the
+reference runs one process per view, scripts/pipes.sh:30-49), so the only parallel strategy is data-parallel
+over views with NO collective on the data path; an optional gather of the per-view results feeds fusion."""
+
+
+def views_for_rank(n_views, rank, world):
+    """Round-robin assignment r -> GPU r mod world (balanced to within one view)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return list(range(rank, n_views, world))
+
+
+def gather_results(local, world, group=None):
+    """Optional terminal gather of {view_id: ndarray} dicts to rank 0 (torch.distributed object gather; gloo or
+    nccl).  Not on the hot path."""
+    if world == 1:
+        return dict(local)
+    import torch.distributed as dist
+    bucket = [None] * world if dist.get_rank(group) == 0 else None
+    dist.gather_object(local, bucket, dst=0, group=group)
+    if bucket is None:
+        return None
+    out = {}
+    for part in bucket:
+        out.update(part)
+    return out
+
+
+def run_sharded(n_views, rank, world, process_view):
+    """Calls process_view(view_id) for this rank's views; returns {view_id: result}."""
+    return {v: process_view(v) for v in views_for_rank(n_views, rank, world)}
