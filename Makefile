@@ -8,8 +8,8 @@ NVFLAGS   := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Iinclude
 PKG       := tsar-mvs_b200
 SRC       := $(PKG)/csrc
 BUILD     := build/obj
-OBJS      := $(BUILD)/context.o $(BUILD)/pm_inst_w11.o $(BUILD)/pm_inst_w11b.o $(BUILD)/pm_inst_w11c.o $(BUILD)/pm_inst_w11d.o $(BUILD)/pm_inst_w11e.o $(BUILD)/pm_inst_w11f.o $(BUILD)/pm_inst_w19.o $(BUILD)/pm_inst_generic.o \
-             $(BUILD)/pm_misc.o
+OBJS      := $(BUILD)/context.o $(BUILD)/pm_inst_w11.o $(BUILD)/pm_inst_w19.o $(BUILD)/pm_inst_generic.o \
+             $(BUILD)/pm_misc.o $(BUILD)/gipuma_shim.o
 HDRS      := $(wildcard $(SRC)/*.cuh $(SRC)/*.h $(SRC)/*.inc include/*.h)
 
 all: $(PKG)/libtsar_b200.so
@@ -21,7 +21,11 @@ $(BUILD)/%.o: $(SRC)/%.cu $(HDRS)
 $(PKG)/libtsar_b200.so: $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
-oracle: oracle/liboracle_cpu.so
+# test harness that plays the reference's host program against the drop-in entry points
+tests/libshim_harness.so: tests/shim_harness.cu $(PKG)/libtsar_b200.so include/tsar_gipuma_abi.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ tests/shim_harness.cu -L$(PKG) -ltsar_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../$(PKG)'
+
+oracle: oracle/liboracle_cpu.so tests/libshim_harness.so
 	bash oracle/build_ref.sh
 
 oracle/liboracle_cpu.so: oracle/oracle_cpu.c oracle/oracle_cpu.h

@@ -187,6 +187,9 @@ int tsar_dbg_tex_sample(tsar_ctx *ctx, int image, int n, const float *xy, float 
 /* Issue-rate microbenchmarks on this GPU: out3 = {FP32 FFMA TFLOP/s, MUFU Gop/s, bilinear fp32
  * texture Gsamples/s}; the measured denominators of the PatchMatch roofline. */
 int tsar_dbg_peaks(tsar_ctx *ctx, float *out3);
+/* Experiment: samples + bilinear fetch rate of the same image stored as f32 / u8-unorm / u16-unorm / f16 texels
+ * (out = 4*n floats, rate4 = Gsamples/s per format). */
+int tsar_dbg_tex_formats(tsar_ctx *ctx, int image, int n, const float *xy, float *out, float *rate4);
 /* Test-only: tsar_eval_planes normally rounds H*(x,y,1) as the reference's real kernels do
  * (fma(m0,x, m1*y) + m2).  The oracle's stand-alone wrapper kernel around pmCostMultiview_cu is compiled
  * by nvcc with the loop-hoisted form (fma(m1,y, m0*x) + m2); wrapper_rounding=1 selects that form so the

@@ -239,3 +239,76 @@ def test_slic_labels_bit_exact(env, cfg, size, enforce):
     assert (mine == ref).all(), f"{(mine != ref).mean():.4%} of labels differ"
     assert len(np.unique(mine)) > 4
     assert (full >= 0).all() and full.max() < (bgrx.shape[0] // size) * (bgrx.shape[1] // size)
+
+
+def test_reference_entry_points_drop_in(env, small):
+    """firstcuda / sliccuda / fakecuda / fillcuda (gipuma.h:2-5) exported by libtsar_b200.so, driven by a harness that
+    plays the reference's host program (managed GlobalState with the reference's layout, float textures in
+    cudaArrays): (a) north-star PatchMatch mode == the engine's own sequence, (b) shipped flow == reference build."""
+    import ctypes as C
+    import os
+    pkg, rb = env
+    L = pkg._lib
+    scene = small
+    so = os.path.join(pc.ROOT, "tests", "libshim_harness.so")
+    assert os.path.exists(so), "tests/libshim_harness.so missing: run `make oracle`"
+    h = C.CDLL(so)
+    from tsar_mvs_b200.engine import cameras_to_struct
+    cams = cameras_to_struct(scene["cams"])
+    params = pkg.make_params(box=11, iterations=2, min_disparity=scene["min_disparity"], max_disparity=scene["max_disparity"])
+    imgs = [np.ascontiguousarray(im, np.float32) for im in scene["images"]]
+    ptrs = (C.c_void_p * len(imgs))(*[im.ctypes.data for im in imgs])
+    sub = (C.c_int * len(scene["subset"]))(*scene["subset"])
+    H, W = imgs[0].shape
+    n = W * H
+
+    def run(shipped, imp_n4=None, imp_disp=None):
+        o_n4, o_cf = np.zeros((H, W, 4), np.float32), np.zeros((H, W), np.float32)
+        o_fd, o_sc = np.zeros((H, W), np.float32), np.zeros((H, W), np.float32)
+        imp_n4 = np.zeros((H, W, 4), np.float32) if imp_n4 is None else np.ascontiguousarray(imp_n4, np.float32)
+        imp_disp = np.zeros((H, W), np.float32) if imp_disp is None else np.ascontiguousarray(imp_disp, np.float32)
+        rc = h.shim_harness_run(W, H, len(imgs), ptrs, cams, C.c_float(scene["cam_f"]), sub, len(scene["subset"]), C.byref(params),
+                                scene["canny"].ctypes.data_as(C.c_void_p), len(scene["region_text"]),
+                                scene["region_text"].ctypes.data_as(C.c_void_p), scene["region_norm4"].ctypes.data_as(C.c_void_p),
+                                int(shipped), imp_n4.ctypes.data_as(C.c_void_p), imp_disp.ctypes.data_as(C.c_void_p),
+                                o_n4.ctypes.data_as(C.c_void_p), o_cf.ctypes.data_as(C.c_void_p), o_fd.ctypes.data_as(C.c_void_p),
+                                o_sc.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        return o_n4, o_cf, o_fd, o_sc
+
+    # (a) north-star mode through the reference's entry points == engine sequence
+    os.environ["TSAR_B200_PATCHMATCH"] = "1"
+    os.environ["TSAR_B200_SEED"] = str(SEED)
+    try:
+        s_n4, s_cf, s_fd, s_sc = run(False)
+    finally:
+        del os.environ["TSAR_B200_PATCHMATCH"]
+    _, eng, _ = pc.make_engines(pkg, scene, iterations=2, variants=())
+    eng.set_regions(scene["region_text"], scene["region_norm4"])
+    eng.upload(L.F_CANNY, scene["canny"])
+    eng.init_planes(SEED); eng.iterate(2, SEED); eng.lrdiff(); eng.getview()
+    cf = eng.download(L.F_CONFID)
+    eng.update_scale_2(); eng.update_scale(); eng.compute_disp()
+    assert pc.frac_bit_exact(s_cf, cf) == 1.0
+    assert pc.frac_bit_exact(s_n4, eng.download(L.F_NORM4)) == 1.0
+    assert pc.frac_bit_exact(s_fd, eng.download(L.F_FAKEDEPTH)) == 1.0
+    assert pc.frac_bit_exact(s_sc, eng.download(L.F_SCALE)) == 1.0
+    eng.close()
+    # (b) shipped flow (imported normals + disparities -> get_disp -> getview -> fake -> fill) == reference build
+    rng = np.random.RandomState(3)
+    wn = rng.normal(size=(H, W, 4)).astype(np.float32)
+    wn[..., :3] /= np.linalg.norm(wn[..., :3], axis=-1, keepdims=True)
+    disp = (scene["cam_f"] / scene["gt_depth"]).astype(np.float32)
+    s_n4, s_cf, s_fd, s_sc = run(True, wn, disp)
+    _, _, refs = pc.make_engines(pkg, scene, iterations=2, variants=("asis",))
+    ref = refs["asis"]
+    ref.set_regions(scene["region_text"], scene["region_norm4"])
+    ref.upload(rb.F_CANNY, scene["canny"])
+    ref.upload(rb.F_NORM4, wn); ref.upload(rb.F_COST, np.ones((H, W), np.float32)); ref.upload(rb.F_DEPTH, disp)
+    ref.get_disp(); ref.getview()
+    assert pc.frac_bit_exact(s_cf, ref.download(rb.F_CONFID)) == 1.0
+    ref.update_scale_2(); ref.update_scale(); ref.compute_disp()
+    assert pc.frac_bit_exact(s_n4, ref.download(rb.F_NORM4)) == 1.0
+    assert pc.frac_bit_exact(s_fd, ref.download(rb.F_FAKEDEPTH)) == 1.0
+    assert pc.frac_bit_exact(s_sc, ref.download(rb.F_SCALE)) == 1.0
+    ref.close()

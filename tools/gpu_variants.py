@@ -12,7 +12,7 @@ import torch
 from tests import parity_common as pc
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
-variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ["a", "b", "c", "d"]
+variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ["u8", "f32"]
 pkg = pc.load_pkg()
 L = pkg._lib
 scene = pkg.scene.make_scene(cfg, backend="torch", device="cuda:0")
@@ -22,7 +22,7 @@ cams = cameras_to_struct(scene["cams"])
 params = pkg.make_params(box=11, iterations=8, min_disparity=scene["min_disparity"], max_disparity=scene["max_disparity"])
 res, base = {}, None
 for v in variants:
-    os.environ["TSAR_B200_W11_VARIANT"] = v
+    os.environ["TSAR_B200_NO_U8"] = "1" if v == "f32" else "0"
     eng = pkg.DepthmapEngine(0)
     eng.set_views_device([t.data_ptr() for t in imgs], scene["W"], scene["H"], cams, scene["subset"], cam_f=scene["cam_f"])
     eng.set_params(params)

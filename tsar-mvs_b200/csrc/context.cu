@@ -4,6 +4,7 @@
 // hardware-filtered source samples + a linear copy of the reference image for the hoisted window
 // terms), cameras, and the LineState arrays of the reference (linestate.h:10-221) as plain device
 // SoA buffers -- no managed memory, no device-wide syncs, everything on one stream.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -36,6 +37,12 @@ struct tsar_ctx {
     // images
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> tex;
+    std::vector<cudaArray_t> arrays8;          // 8-bit copies of the views (sampling fast path)
+    std::vector<cudaTextureObject_t> tex8;
+    unsigned char *stage8 = nullptr;           // staging buffer for the float -> u8 conversion
+    int *d_flag = nullptr;
+    int use_u8 = 0;                            // every image is 8-bit valued: sample the 8-bit textures
+    bool allow_u8 = true;                      // env TSAR_B200_NO_U8=1 switches the fast path off
     int arr_w = 0, arr_h = 0;
     float *ref_img = nullptr;
     cudaTextureObject_t *d_tex = nullptr;
@@ -91,6 +98,20 @@ struct tsar_ctx {
 static const char *kVersion = "tsar_b200 0.1 (sm_100a)";
 
 // ------------------------------------------------------------------------------------------------
+// 8-bit copies of the views
+// ------------------------------------------------------------------------------------------------
+// flag |= 1 if any value is not an integer in [0, 255]; writes the 8-bit copy on the way
+__global__ void to_u8_kernel(const float *__restrict__ img, unsigned char *__restrict__ out, size_t n, int *flag) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = img[i];
+    const float r = rintf(v);
+    const bool ok = (v == r) && (v >= 0.0f) && (v <= 255.0f);
+    out[i] = ok ? (unsigned char)r : 0;
+    if (!ok) *flag = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------------
 static size_t win_smem_bytes(int nt, int ns) { return (size_t)ns * nt * sizeof(float2) + (size_t)ns * sizeof(float); }
@@ -99,15 +120,7 @@ static const PmVariant *pick_variant(const tsar_params &p, bool init) {
     const int hs = p.box_hsize, vs = p.box_vsize;
     const int hr = init ? hs / 2 : (hs - 1) / 2, vr = init ? vs / 2 : (vs - 1) / 2;
     const bool fast_comb = (p.cost_comb == 1 && p.n_best <= 2);
-    if (fast_comb && hr == vr && hr == 5) {
-        const char *v = getenv("TSAR_B200_W11_VARIANT");  // launch-shape experiments; results are identical
-        if (v && v[0] == 'b') return &pm_variant_w11b;
-        if (v && v[0] == 'c') return &pm_variant_w11c;
-        if (v && v[0] == 'd') return &pm_variant_w11d;
-        if (v && v[0] == 'e') return &pm_variant_w11e;
-        if (v && v[0] == 'f') return &pm_variant_w11f;
-        return &pm_variant_w11;
-    }
+    if (fast_comb && hr == vr && hr == 5) return &pm_variant_w11;
     if (fast_comb && hr == vr && hr == 9) return &pm_variant_w19;
     return &pm_variant_generic;
 }
@@ -141,6 +154,7 @@ static int rebuild_constants(tsar_ctx *ctx) {
         const int id = ctx->subset[i];
         const tsar_camera &s = ctx->cams[id];
         c.tex[i] = ctx->tex[id];
+        c.tex8[i] = ctx->use_u8 ? ctx->tex8[id] : 0;
         c.view_id[i] = id;
         for (int k = 0; k < 9; k++) { c.view[i].R[k] = s.R[k]; c.view[i].K[k] = s.K[k]; }
         for (int k = 0; k < 3; k++) c.view[i].t[k] = s.t4[k];
@@ -177,6 +191,11 @@ static void free_state(tsar_ctx *ctx) {
 static void free_images(tsar_ctx *ctx) {
     for (auto t : ctx->tex) cudaDestroyTextureObject(t);
     for (auto a : ctx->arrays) cudaFreeArray(a);
+    for (auto t : ctx->tex8) cudaDestroyTextureObject(t);
+    for (auto a : ctx->arrays8) cudaFreeArray(a);
+    ctx->tex8.clear();
+    ctx->arrays8.clear();
+    cudaFree(ctx->stage8); ctx->stage8 = nullptr;
     ctx->tex.clear();
     ctx->arrays.clear();
     ctx->arr_w = ctx->arr_h = 0;
@@ -264,7 +283,7 @@ static int launch_checker(tsar_ctx *ctx, int mode, int colour) {
         CK(cudaEventCreate(&p0)); CK(cudaEventCreate(&p1));
         CK(cudaEventRecord(p0, ctx->stream));
     }
-    CK(ctx->variant->checker(mode, ctx->pm, ctx->ref_img, a, ctx->stream));
+    CK(ctx->variant->checker(ctx->use_u8, mode, ctx->pm, ctx->ref_img, a, ctx->stream));
     if (ctx->profiling) {
         CK(cudaEventRecord(p1, ctx->stream));
         ctx->prof_events.emplace_back(p0, p1);
@@ -317,6 +336,8 @@ int tsar_create(int device, void *stream, tsar_ctx **out) {
     cudaEventCreate(&ctx->ev1);
     const char *uf = getenv("TSAR_B200_UNFUSED");
     ctx->fused = !(uf && uf[0] == '1');
+    const char *n8 = getenv("TSAR_B200_NO_U8");
+    ctx->allow_u8 = !(n8 && n8[0] == '1');
     *out = ctx;
     return TSAR_OK;
 }
@@ -328,7 +349,7 @@ int tsar_destroy(tsar_ctx *ctx) {
     free_state(ctx);
     free_images(ctx);
     cudaFree(ctx->d_tex); cudaFree(ctx->d_cams); cudaFree(ctx->rng); cudaFree(ctx->scratch);
-    cudaFree(ctx->region_text); cudaFree(ctx->region_plane);
+    cudaFree(ctx->region_text); cudaFree(ctx->region_plane); cudaFree(ctx->d_flag);
     slic_free(ctx->slic);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -391,6 +412,53 @@ int tsar_set_views(tsar_ctx *ctx, int W, int H, int n_images, const float *const
     for (int i = 0; i < n_images; i++)
         CK(cudaMemcpy2DToArrayAsync(ctx->arrays[i], 0, 0, images[i], (size_t)W * 4, (size_t)W * 4, H, kind, ctx->stream));
     CK(cudaMemcpyAsync(ctx->ref_img, images[0], n * 4, kind, ctx->stream));
+    // 8-bit copies: the reference's inputs are 8-bit grey images converted to float (main.cpp:1423), for which an
+    // 8-bit texture gives bit-identical bilinear samples at a quarter of the texel traffic (pm_core.cuh, view_cost)
+    ctx->use_u8 = 0;
+    if (ctx->allow_u8) {
+        if ((int)ctx->arrays8.size() != n_images) {
+            for (auto t : ctx->tex8) cudaDestroyTextureObject(t);
+            for (auto a : ctx->arrays8) cudaFreeArray(a);
+            ctx->tex8.clear(); ctx->arrays8.clear();
+            cudaFree(ctx->stage8); ctx->stage8 = nullptr;
+            cudaChannelFormatDesc c8 = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+            for (int i = 0; i < n_images; i++) {
+                cudaArray_t a;
+                CK(cudaMallocArray(&a, &c8, W, H));
+                ctx->arrays8.push_back(a);
+                cudaResourceDesc rd;
+                memset(&rd, 0, sizeof(rd));
+                rd.resType = cudaResourceTypeArray;
+                rd.res.array.array = a;
+                cudaTextureDesc td;
+                memset(&td, 0, sizeof(td));
+                td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+                td.filterMode = cudaFilterModeLinear;
+                td.readMode = cudaReadModeNormalizedFloat;
+                td.normalizedCoords = 0;
+                cudaTextureObject_t t;
+                CK(cudaCreateTextureObject(&t, &rd, &td, NULL));
+                ctx->tex8.push_back(t);
+            }
+            CK(cudaMalloc(&ctx->stage8, n));
+            if (!ctx->d_flag) CK(cudaMalloc(&ctx->d_flag, sizeof(int)));
+        }
+        CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+        float *lin = nullptr;  // linear device copy of view i (view 0 is already in ref_img)
+        if (!on_device) CK(cudaMalloc(&lin, n * 4));
+        for (int i = 0; i < n_images; i++) {
+            const float *src = on_device ? images[i] : lin;
+            if (!on_device) CK(cudaMemcpyAsync(lin, images[i], n * 4, cudaMemcpyHostToDevice, ctx->stream));
+            to_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->stage8, n, ctx->d_flag);
+            CK(cudaMemcpy2DToArrayAsync(ctx->arrays8[i], 0, 0, ctx->stage8, (size_t)W, (size_t)W, H, cudaMemcpyDeviceToDevice, ctx->stream));
+            ctx->launches++;
+        }
+        int flag = 1;
+        CK(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (lin) cudaFree(lin);
+        ctx->use_u8 = (flag == 0);
+    }
     ctx->W = W; ctx->H = H; ctx->n_images = n_images; ctx->V = V;
     ctx->cams.assign(cams, cams + n_images);
     ctx->cam_f = cam_f;
@@ -433,7 +501,7 @@ int tsar_init_planes(tsar_ctx *ctx, uint64_t seed) {
     if (rc) return rc;
     if ((rc = zero_state(ctx, false))) return rc;
     if ((rc = make_rng_table(ctx, seed))) return rc;
-    CK(ctx->variant_init->init(ctx->pm_init, ctx->ref_img, ctx->rng, ctx->rng_len, ctx->plane[0], ctx->cost[0], ctx->stream));
+    CK(ctx->variant_init->init(ctx->use_u8, ctx->pm_init, ctx->ref_img, ctx->rng, ctx->rng_len, ctx->plane[0], ctx->cost[0], ctx->stream));
     ctx->launches++;
     ctx->cur[0] = ctx->cur[1] = 0;
     ctx->have_planes = true;
@@ -448,7 +516,7 @@ int tsar_load_planes(tsar_ctx *ctx, const float *norm4, const float *cost) {
     CK(cudaMemcpyAsync(ctx->plane[0], norm4, n * 16, cudaMemcpyHostToDevice, ctx->stream));
     if (cost) CK(cudaMemcpyAsync(ctx->cost[0], cost, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     else {
-        CK(ctx->variant->cost_of_state(ctx->pm, ctx->ref_img, ctx->plane[0], ctx->cost[0], ctx->stream));
+        CK(ctx->variant->cost_of_state(ctx->use_u8, ctx->pm, ctx->ref_img, ctx->plane[0], ctx->cost[0], ctx->stream));
         ctx->launches++;
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -510,7 +578,7 @@ int tsar_eval_planes(tsar_ctx *ctx, int n, const int *xy, const float *planes, f
     float *dr = (float *)(base + (size_t)n * 32);
     CK(cudaMemcpyAsync(dxy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dpl, planes, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
-    CK(ctx->variant->eval(ctx->eval_wrapper_rounding, ctx->pm, ctx->ref_img, n, dxy, dpl, dc, db, dr, ctx->stream));
+    CK(ctx->variant->eval(ctx->use_u8, ctx->eval_wrapper_rounding, ctx->pm, ctx->ref_img, n, dxy, dpl, dc, db, dr, ctx->stream));
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(cost, dc, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -803,6 +871,68 @@ int tsar_profile_read(tsar_ctx *ctx, float *checker_ms_total, int *n_launches) {
 int tsar_dbg_eval_rounding(tsar_ctx *ctx, int wrapper_rounding) {
     if (!ctx) return TSAR_ERR_ARG;
     ctx->eval_wrapper_rounding = wrapper_rounding ? 1 : 0;
+    return TSAR_OK;
+}
+
+// Experiment: the same image as 8-bit (normalised-float read), 16-bit unorm and fp16 textures; samples at the given
+// coordinates and bilinear-fetch throughput per format.  out = 4 arrays of n floats (f32, u8, u16, f16 texels),
+// rate4 = Gsamples/s per format with a warp-local access pattern.
+int tsar_dbg_tex_formats(tsar_ctx *ctx, int image, int n, const float *xy, float *out, float *rate4) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    const int W = ctx->W, H = ctx->H;
+    std::vector<float> host((size_t)W * H);
+    CK(cudaMemcpy2DFromArray(host.data(), (size_t)W * 4, ctx->arrays[image], 0, 0, (size_t)W * 4, H, cudaMemcpyDeviceToHost));
+    std::vector<unsigned char> h8((size_t)W * H);
+    std::vector<unsigned short> h16((size_t)W * H), hf16((size_t)W * H);
+    for (size_t i = 0; i < host.size(); i++) {
+        h8[i] = (unsigned char)host[i];
+        h16[i] = (unsigned short)(host[i] * 257.0f);
+        hf16[i] = __half_as_ushort(__float2half(host[i]));
+    }
+    cudaTextureObject_t tex[4];
+    cudaArray_t arr[3];
+    tex[0] = ctx->tex[image];
+    cudaChannelFormatDesc cds[3] = {cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned),
+                                    cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned),
+                                    cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindFloat)};
+    const void *srcs[3] = {h8.data(), h16.data(), hf16.data()};
+    const size_t esz[3] = {1, 2, 2};
+    for (int k = 0; k < 3; k++) {
+        CK(cudaMallocArray(&arr[k], &cds[k], W, H));
+        CK(cudaMemcpy2DToArray(arr[k], 0, 0, srcs[k], W * esz[k], W * esz[k], H, cudaMemcpyHostToDevice));
+        cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray; rd.res.array.array = arr[k];
+        cudaTextureDesc td; memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = (k < 2) ? cudaReadModeNormalizedFloat : cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        CK(cudaCreateTextureObject(&tex[k + 1], &rd, &td, NULL));
+    }
+    if ((rc = ensure_scratch(ctx, (size_t)n * 12))) return rc;
+    float2 *dxy = (float2 *)ctx->scratch;
+    float *dout = (float *)((unsigned char *)ctx->scratch + (size_t)n * 8);
+    CK(cudaMemcpyAsync(dxy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    for (int k = 0; k < 4; k++) {
+        dbg_tex_sample_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(tex[k], n, dxy, dout);
+        CK(cudaMemcpyAsync(out + (size_t)k * n, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float best = 0.f;
+        for (int rep = 0; rep < 3; rep++) {
+            float ms;
+            CK(cudaEventRecord(ctx->ev0, ctx->stream));
+            dbg_tex_kernel<<<sms * 8, 256, 0, ctx->stream>>>(tex[k], dout, 256, W, H);
+            CK(cudaEventRecord(ctx->ev1, ctx->stream));
+            CK(cudaEventSynchronize(ctx->ev1));
+            CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            best = std::max(best, (float)((double)sms * 8 * 256 * 256 * 4 / (ms * 1e-3) / 1e9));
+        }
+        rate4[k] = best;
+    }
+    for (int k = 0; k < 3; k++) { cudaDestroyTextureObject(tex[k + 1]); cudaFreeArray(arr[k]); }
     return TSAR_OK;
 }
 

@@ -1,0 +1,190 @@
+// gipuma_shim.cu -- the reference's entry points (gipuma.h:2-5) on top of the C ABI of include/tsar_b200.h.
+//
+// The caller (the reference's runGipuma, main.cpp:1268-1866) owns a managed-memory GlobalState: textures and
+// cudaArrays of all views, cameras, parameters, and the per-pixel LineState arrays it fills on the host
+// between the four calls.  Each shim mirrors what the call needs into the device-resident context, runs the
+// kernels and writes the results back into the caller's arrays; nothing here touches managed memory from a
+// kernel.  See include/tsar_gipuma_abi.h for the contract of every call.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <vector>
+
+#include "../../include/tsar_b200.h"
+#include "../../include/tsar_gipuma_abi.h"
+
+namespace {
+
+typedef tsar_abi::GlobalState AbiState;
+
+struct ShimCtx {
+    tsar_ctx *ctx = nullptr;
+    bool views = false;
+    int n_regions = 0;
+};
+std::map<const void *, ShimCtx> g_ctx;
+
+int fail(tsar_ctx *ctx, const char *what, int rc) {
+    fprintf(stderr, "[tsar_b200 shim] %s failed (%d): %s\n", what, rc, ctx ? tsar_last_error(ctx) : "no context");
+    return rc;
+}
+
+void copy9(float *dst, const float *src) { for (int i = 0; i < 9; i++) dst[i] = src[i]; }
+
+// Mirrors images, cameras, view selection and parameters of gs into the context (once per GlobalState).
+int ensure_views(AbiState &gs, ShimCtx &s) {
+    if (!s.ctx) {
+        int dev = 0;
+        cudaGetDevice(&dev);  // the reference relies on the current device (selectCudaDevice, main.cpp:1264)
+        int rc = tsar_create(dev, nullptr, &s.ctx);
+        if (rc) return fail(nullptr, "tsar_create", rc);
+    }
+    if (s.views) return 0;
+    cudaDeviceSynchronize();
+    const tsar_abi::CameraParameters_cu &cp = *gs.cameras;
+    const int W = cp.cols, H = cp.rows, V = cp.viewSelectionSubsetNumber;
+    int n_images = 1;
+    for (int i = 0; i < V; i++) n_images = cp.viewSelectionSubset[i] + 1 > n_images ? cp.viewSelectionSubset[i] + 1 : n_images;
+    std::vector<tsar_camera> cams(n_images);
+    for (int i = 0; i < n_images; i++) {
+        const tsar_abi::Camera_cu &c = cp.cameras[i];
+        tsar_camera &o = cams[i];
+        copy9(o.K, c.K); copy9(o.K_inv, c.K_inv); copy9(o.R, c.R); copy9(o.R_orig, c.R_orig);
+        copy9(o.R_orig_inv, c.R_orig_inv); copy9(o.M_inv, c.M_inv);
+        o.t4[0] = c.t4.x; o.t4[1] = c.t4.y; o.t4[2] = c.t4.z;
+        o.P_col34[0] = c.P_col34.x; o.P_col34[1] = c.P_col34.y; o.P_col34[2] = c.P_col34.z;
+        o.C4[0] = c.C4.x; o.C4[1] = c.C4.y; o.C4[2] = c.C4.z;
+        o.fx = c.fx; o.fy = c.fy; o.f = c.f; o.alpha = c.alpha; o.baseline = c.baseline;
+        o.depthMin = c.depthMin; o.depthMax = c.depthMax;
+    }
+    // the caller uploaded the images into cudaArrays (addImageToTextureFloatGray, main.cpp:1190-1228)
+    std::vector<float *> dev_imgs(n_images, nullptr);
+    for (int i = 0; i < n_images; i++) {
+        if (cudaMalloc(&dev_imgs[i], (size_t)W * H * 4) != cudaSuccess ||
+            cudaMemcpy2DFromArray(dev_imgs[i], (size_t)W * 4, gs.cuArray[i], 0, 0, (size_t)W * 4, H, cudaMemcpyDeviceToDevice) != cudaSuccess) {
+            fprintf(stderr, "[tsar_b200 shim] reading view %d from its cudaArray failed: %s\n", i, cudaGetErrorString(cudaGetLastError()));
+            return TSAR_ERR_CUDA;
+        }
+    }
+    std::vector<int> subset(cp.viewSelectionSubset, cp.viewSelectionSubset + V);
+    int rc = tsar_set_views(s.ctx, W, H, n_images, dev_imgs.data(), 1, cams.data(), cp.f, subset.data(), V);
+    for (float *p : dev_imgs) cudaFree(p);
+    if (rc) return fail(s.ctx, "tsar_set_views", rc);
+    const tsar_abi::AlgorithmParameters &ap = *gs.params;
+    tsar_params p;
+    p.box_hsize = ap.box_hsize; p.box_vsize = ap.box_vsize; p.iterations = ap.iterations; p.n_best = ap.n_best;
+    p.cost_comb = ap.cost_comb; p.min_disparity = ap.min_disparity; p.max_disparity = ap.max_disparity;
+    p.color_processing = ap.color_processing ? 1 : 0;
+    if ((rc = tsar_set_params(s.ctx, &p))) return fail(s.ctx, "tsar_set_params", rc);
+    s.views = true;
+    return 0;
+}
+
+int up(ShimCtx &s, int field, const void *src, size_t bytes) {
+    int rc = tsar_upload(s.ctx, field, src, bytes);
+    return rc ? fail(s.ctx, "tsar_upload", rc) : 0;
+}
+int down(ShimCtx &s, int field, void *dst, size_t bytes) {
+    int rc = tsar_download(s.ctx, field, dst, bytes);
+    return rc ? fail(s.ctx, "tsar_download", rc) : 0;
+}
+
+// region table: cannylines->text / ->norm4; its length is not stored anywhere in GlobalState (Cannyresize(n),
+// main.cpp:571), so it is taken from the largest label in lines->canny
+int ensure_regions(AbiState &gs, ShimCtx &s, size_t n) {
+    int maxlab = 0;
+    for (size_t i = 0; i < n; i++) maxlab = (int)gs.lines->canny[i] > maxlab ? (int)gs.lines->canny[i] : maxlab;
+    s.n_regions = maxlab + 1;
+    int rc = tsar_set_regions(s.ctx, s.n_regions, gs.cannylines->text, (const float *)gs.cannylines->norm4);
+    if (rc) return fail(s.ctx, "tsar_set_regions", rc);
+    return up(s, TSAR_F_CANNY, gs.lines->canny, n * 4);
+}
+
+}  // namespace
+
+int firstcuda(GlobalState &gs_) {
+    tsar_abi::GlobalState &gs = reinterpret_cast<tsar_abi::GlobalState &>(gs_);
+    ShimCtx &s = g_ctx[&gs];
+    int rc = ensure_views(gs, s);
+    if (rc) return rc;
+    const size_t n = (size_t)gs.cameras->cols * gs.cameras->rows;
+    const char *pm = getenv("TSAR_B200_PATCHMATCH");
+    if (pm && pm[0] == '1') {
+        const char *sd = getenv("TSAR_B200_SEED");
+        const uint64_t seed = sd ? strtoull(sd, nullptr, 10) : 20240601ULL;
+        if ((rc = tsar_init_planes(s.ctx, seed))) return fail(s.ctx, "tsar_init_planes", rc);
+        if ((rc = tsar_iterate(s.ctx, gs.params->iterations, seed, nullptr))) return fail(s.ctx, "tsar_iterate", rc);
+        if ((rc = tsar_lrdiff(s.ctx))) return fail(s.ctx, "tsar_lrdiff", rc);
+        if ((rc = down(s, TSAR_F_COST, gs.lines->c, n * 4))) return rc;
+        if ((rc = down(s, TSAR_F_RATIO, gs.lines->ratio, n * 4))) return rc;
+        if ((rc = down(s, TSAR_F_BEVIEW, gs.lines->beview, n * 4))) return rc;
+        if ((rc = down(s, TSAR_F_LRDIFF, gs.lines->lrdiff, n * 4))) return rc;
+    } else {
+        // shipped flow: normals/disparities imported by the caller (main.cpp:1476-1488), then gipuma_get_disp
+        if ((rc = up(s, TSAR_F_NORM4, gs.lines->norm4, n * 16))) return rc;
+        if ((rc = up(s, TSAR_F_COST, gs.lines->c, n * 4))) return rc;
+        if ((rc = up(s, TSAR_F_DEPTH, gs.lines->depth, n * 4))) return rc;
+        if ((rc = tsar_get_disp(s.ctx))) return fail(s.ctx, "tsar_get_disp", rc);
+    }
+    return down(s, TSAR_F_NORM4, gs.lines->norm4, n * 16);
+}
+
+int sliccuda(GlobalState &gs_) {
+    tsar_abi::GlobalState &gs = reinterpret_cast<tsar_abi::GlobalState &>(gs_);
+    ShimCtx &s = g_ctx[&gs];
+    int rc = ensure_views(gs, s);
+    if (rc) return rc;
+    const size_t n = (size_t)gs.cameras->cols * gs.cameras->rows;
+    cudaDeviceSynchronize();
+    if ((rc = up(s, TSAR_F_NORM4, gs.lines->norm4, n * 16))) return rc;
+    if ((rc = up(s, TSAR_F_COST, gs.lines->c, n * 4))) return rc;
+    if ((rc = up(s, TSAR_F_LRDIFF, gs.lines->lrdiff, n * 4))) return rc;
+    if ((rc = tsar_getview(s.ctx))) return fail(s.ctx, "tsar_getview", rc);
+    if ((rc = down(s, TSAR_F_CONFID, gs.lines->confid, n * 4))) return rc;
+    return down(s, TSAR_F_DEPTH, gs.lines->depth, n * 4);
+}
+
+int fakecuda(GlobalState &gs_) {
+    tsar_abi::GlobalState &gs = reinterpret_cast<tsar_abi::GlobalState &>(gs_);
+    ShimCtx &s = g_ctx[&gs];
+    int rc = ensure_views(gs, s);
+    if (rc) return rc;
+    const size_t n = (size_t)gs.cameras->cols * gs.cameras->rows;
+    cudaDeviceSynchronize();
+    if ((rc = ensure_regions(gs, s, n))) return rc;
+    if ((rc = up(s, TSAR_F_FAKEDEPTH, gs.lines->fakedepth, n * 4))) return rc;
+    if ((rc = tsar_update_scale_2(s.ctx))) return fail(s.ctx, "tsar_update_scale_2", rc);
+    return down(s, TSAR_F_FAKEDEPTH, gs.lines->fakedepth, n * 4);
+}
+
+int fillcuda(GlobalState &gs_) {
+    tsar_abi::GlobalState &gs = reinterpret_cast<tsar_abi::GlobalState &>(gs_);
+    ShimCtx &s = g_ctx[&gs];
+    int rc = ensure_views(gs, s);
+    if (rc) return rc;
+    const size_t n = (size_t)gs.cameras->cols * gs.cameras->rows;
+    cudaDeviceSynchronize();
+    if ((rc = ensure_regions(gs, s, n))) return rc;
+    if ((rc = up(s, TSAR_F_NORM4, gs.lines->norm4, n * 16))) return rc;
+    if ((rc = up(s, TSAR_F_COST, gs.lines->c, n * 4))) return rc;
+    if ((rc = up(s, TSAR_F_SCALE, gs.lines->scale, n * 4))) return rc;
+    if ((rc = up(s, TSAR_F_DEPTH, gs.lines->depth, n * 4))) return rc;
+    if ((rc = tsar_update_scale(s.ctx))) return fail(s.ctx, "tsar_update_scale", rc);
+    if ((rc = down(s, TSAR_F_SCALE, gs.lines->scale, n * 4))) return rc;
+    if ((rc = down(s, TSAR_F_DEPTH, gs.lines->depth, n * 4))) return rc;
+    if ((rc = tsar_compute_disp(s.ctx))) return fail(s.ctx, "tsar_compute_disp", rc);
+    if ((rc = down(s, TSAR_F_COST, gs.lines->c, n * 4))) return rc;
+    return down(s, TSAR_F_NORM4, gs.lines->norm4, n * 16);
+}
+
+// release the context mirrored for a GlobalState (the reference leaks gs.cs instead, gipuma.cu:1775, Q17)
+extern "C" int tsar_shim_release(const void *gs) {
+    auto it = g_ctx.find(gs);
+    if (it == g_ctx.end()) return TSAR_OK;
+    tsar_destroy(it->second.ctx);
+    g_ctx.erase(it);
+    return TSAR_OK;
+}

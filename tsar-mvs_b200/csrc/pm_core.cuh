@@ -26,11 +26,6 @@
 #define PM_FAST_UNROLL(n1) (((n1) + 1) / 2)
 #endif
 
-// columns of the checkerboard tile covered by one warp (32 = the reference's mapping)
-#ifndef PM_WARP_COLS
-#define PM_WARP_COLS 32
-#endif
-
 namespace tsar {
 
 constexpr int kMaxViews = 32;
@@ -59,7 +54,8 @@ struct PmConst {
     float baseline;        // cameras[0].baseline
     float depthMin, depthMax;
     float min_disp, max_disp;
-    cudaTextureObject_t tex[kMaxViews];  // source view textures, order of viewSelectionSubset
+    cudaTextureObject_t tex[kMaxViews];  // source view textures (fp32 texels), order of viewSelectionSubset
+    cudaTextureObject_t tex8[kMaxViews]; // the same views as 8-bit unorm textures (valid when every image is 8-bit valued)
     int view_id[kMaxViews];              // viewSelectionSubset[i]
     ViewC view[kMaxViews];
 };
@@ -158,12 +154,19 @@ __device__ __forceinline__ void homography(const PmConst &c, const ViewC &v, con
 //   true:  fadd(m2, fma(m1, py, m0*px))  -- the loop-hoisted form nvcc happens to emit for the oracle's
 //          stand-alone wrapper kernel (oracle/ref_driver.cu: ref_eval_kernel).  Test-only switch so the
 //          unit-level parity test can demand bit equality against that wrapper.
-template <int NT, int N1, bool PXF>
+//
+// U8: fetch from the 8-bit copy of the source view.  The texture unit's bilinear result for 8-bit texels,
+// read as normalised float v, satisfies rint(v * 255 * 256) == N with N / 256 exactly the fp32-texel result
+// (weights have 8 fractional bits; calibrated on B200: 400k samples incl. borders, 100 % identical).  The
+// window sums are carried in units of N (i.e. scaled by 2^8 / 2^16, exact in binary floating point) and
+// scaled back once per evaluation, so costs are bit-identical to the fp32-texture path while each warp-wide
+// fetch moves a quarter of the texel bytes through the L1TEX data pipe (the measured limiter).
+template <int NT, int N1, bool PXF, bool U8>
 __device__ __forceinline__ float view_cost(const PmConst &c, int vi, int x, int y, const float4 &pl,
                                            const float2 *__restrict__ wt_thread, const RefStats &rs) {
     float Hm[9];
     homography(c, c.view[vi], pl, Hm);
-    const cudaTextureObject_t tex = c.tex[vi];
+    const cudaTextureObject_t tex = U8 ? c.tex8[vi] : c.tex[vi];
     float s_s = 0.f, s_ss = 0.f, s_rs = 0.f;
     const int n1x = N1 ? N1 : c.n1x, n1y = N1 ? N1 : c.n1y;
     const int hrad = N1 ? N1 - 1 : c.hrad, vrad = N1 ? N1 - 1 : c.vrad;
@@ -203,7 +206,8 @@ __device__ __forceinline__ float view_cost(const PmConst &c, int vi, int x, int 
                 const float r = refined_rcp(Z);
                 const float xs_ = fadd(div_refined(X, Z, r), 0.5f);
                 const float ys_ = fadd(div_refined(Y, Z, r), 0.5f);
-                const float src = tex2D<float>(tex, xs_, ys_);  // hardware bilinear, clamp
+                float src = tex2D<float>(tex, xs_, ys_);  // hardware bilinear, clamp
+                if (U8) src = fsub(ffma(src, 65280.0f, 12582912.0f), 12582912.0f);  // N = rint(v * 255 * 256)
                 const float2 w = wt_thread[k * NT];            // (w, w*ref)
                 const float ts = fmul(src, w.x);
                 s_s = fadd(s_s, ts);            // gipuma.cu:272
@@ -222,7 +226,8 @@ __device__ __forceinline__ float view_cost(const PmConst &c, int vi, int x, int 
                 const float X = fadd(Hm[2], PXF ? ffma(Hm[1], py, a0) : ffma(Hm[0], px, fmul(Hm[1], py)));
                 const float Y = fadd(Hm[5], PXF ? ffma(Hm[4], py, a1) : ffma(Hm[3], px, fmul(Hm[4], py)));
                 const float Z = fadd(Hm[8], PXF ? ffma(Hm[7], py, a2) : ffma(Hm[6], px, fmul(Hm[7], py)));
-                const float src = tex2D<float>(tex, fadd(fdiv(X, Z), 0.5f), fadd(fdiv(Y, Z), 0.5f));
+                float src = tex2D<float>(tex, fadd(fdiv(X, Z), 0.5f), fadd(fdiv(Y, Z), 0.5f));
+                if (U8) src = fsub(ffma(src, 65280.0f, 12582912.0f), 12582912.0f);
                 const float2 w = wt_thread[k * NT];
                 const float ts = fmul(src, w.x);
                 s_s = fadd(s_s, ts);
@@ -231,6 +236,7 @@ __device__ __forceinline__ float view_cost(const PmConst &c, int vi, int x, int 
             }
         }
     }
+    if (U8) { s_s = fmul(s_s, 0.00390625f); s_rs = fmul(s_rs, 0.00390625f); s_ss = fmul(s_ss, 1.52587890625e-05f); }
     const float ss = fmul(rs.inv, s_s);
     const float var_src = ffma(rs.inv, s_ss, -fmul(ss, ss));
     const float rsn = fmul(rs.inv, s_rs);
@@ -252,7 +258,7 @@ struct MvResult {
 // GENERIC = false: only the two smallest costs are ever read (cost_comb == COMB_BEST_N and
 // n_best <= 2, the setting of every run script), kept in registers.  GENERIC = true: any n_best /
 // COMB_ALL through the reference's full insertion sort (local-memory arrays, as the reference).
-template <int NT, int N1, bool GENERIC, bool PXF = false>
+template <int NT, int N1, bool GENERIC, bool PXF = false, bool U8 = false>
 __device__ __forceinline__ MvResult multiview_cost(const PmConst &c, int x, int y, const float4 &pl,
                                                    const float2 *__restrict__ wt_thread, const RefStats &rs) {
     MvResult out;
@@ -260,7 +266,7 @@ __device__ __forceinline__ MvResult multiview_cost(const PmConst &c, int x, int 
         float s0 = __int_as_float(0x7f800000), s1 = __int_as_float(0x7f800000);
         int nvalid = 0, bidx = -1;
         for (int vi = 0; vi < c.V; vi++) {
-            float cv = view_cost<NT, N1, PXF>(c, vi, x, y, pl, wt_thread, rs);
+            float cv = view_cost<NT, N1, PXF, U8>(c, vi, x, y, pl, wt_thread, rs);
             if (cv < kMaxCost) nvalid++;
             else cv = kMaxCost;
             if (cv < s0) { s1 = s0; s0 = cv; bidx = vi; }
@@ -283,7 +289,7 @@ __device__ __forceinline__ MvResult multiview_cost(const PmConst &c, int x, int 
         float cv[kMaxViews], orig[kMaxViews];
         int nvalid = 0;
         for (int vi = 0; vi < c.V; vi++) {
-            float v = view_cost<NT, N1, PXF>(c, vi, x, y, pl, wt_thread, rs);
+            float v = view_cost<NT, N1, PXF, U8>(c, vi, x, y, pl, wt_thread, rs);
             if (v < kMaxCost) nvalid++;
             else v = kMaxCost;
             cv[vi] = v; orig[vi] = v;

@@ -31,7 +31,7 @@ __device__ __forceinline__ void fill_spatial_table(const PmConst &c, float *sp, 
 // ---------------------------------------------------------------------------------------------
 // (1) random plane initialisation -- gipuma_init_cu2 (gipuma.cu:679-729)
 // ---------------------------------------------------------------------------------------------
-template <int NT, int MINB, int N1, bool GEN>
+template <int NT, int MINB, int N1, bool GEN, bool U8>
 __global__ void __launch_bounds__(NT, MINB) pm_init_kernel(const __grid_constant__ PmConst c, const float *__restrict__ ref,
                                                      const uint32_t *__restrict__ rng, int rng_len,
                                                      float4 *__restrict__ plane, float *__restrict__ cost) {
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_init_kernel(const __grid_constant
     const float depth = fdiv(fmul(c.f_cam0, c.baseline), disp);                  // :712
     float4 pl = make_float4(nx, ny, nz, 0.f);
     pl.w = plane_d(c, nx, ny, nz, x, y, depth);                                  // :715
-    const MvResult r = multiview_cost<NT, N1, GEN>(c, x, y, pl, wt, rs);
+    const MvResult r = multiview_cost<NT, N1, GEN, false, U8>(c, x, y, pl, wt, rs);
     const size_t p = (size_t)y * c.W + x;
     plane[p] = pl;
     cost[p] = r.cost;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_init_kernel(const __grid_constant
 // colours), the thread's own result goes to `*_out` (which may alias `*_in` when DO_SP is false).
 // ---------------------------------------------------------------------------------------------
 
-template <int NT, int MINB, int N1, bool GEN, bool DO_SP, bool DO_PR>
+template <int NT, int MINB, int N1, bool GEN, bool U8, bool DO_SP, bool DO_PR>
 __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_constant__ PmConst c,
                                                         const float *__restrict__ ref, const CheckerArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -90,17 +90,10 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
     fill_spatial_table<N1>(c, sm.sp, tid, NT);
     __syncthreads();
     const int W = c.W, H = c.H;
-    // Pixel of this thread inside the CTA's tile of 32 columns x 2*(NT/32) rows.  The reference maps a warp
-    // to 32 consecutive columns of one row pair (gipuma.cu:1099-1103); which thread takes which pixel does
-    // not change any result (pixels of one colour are independent), but a more compact warp footprint
-    // (PM_WARP_COLS = 16 or 8 columns x 2 or 4 row pairs) lowers the number of texture-cache wavefronts
-    // each warp-wide fetch needs.
-    constexpr int WC = PM_WARP_COLS;          // columns per warp: 32, 16 or 8
-    constexpr int WPR = 32 / WC;              // warps side by side in the 32-column tile
-    const int lane = threadIdx.x, warp = threadIdx.y;
-    const int x = blockIdx.x * 32 + (warp % WPR) * WC + (lane % WC);
-    const int rowpair = (warp / WPR) * (32 / WC) + (lane / WC);
-    const int y = (blockIdx.y * (NT / 32) + rowpair) * 2 + ((x + a.colour) & 1);
+    // block = 32 columns x (NT/32) row pairs; lane parity selects the row of the pair exactly as the reference's
+    // wrappers do (gipuma.cu:1099-1103).  (More compact warp footprints were measured: no difference.)
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = (blockIdx.y * (NT / 32) + threadIdx.y) * 2 + ((x + a.colour) & 1);
     if (x >= W || y >= H || y >= c.y_limit) return;
     const int own = a.colour;
     const int pidx = y * W + x;
@@ -252,7 +245,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
             deltaN = fmul(deltaN, 0.25f);
         }
         if (eval) {
-            const MvResult r = multiview_cost<NT, N1, GEN>(c, x, y, cand, wt, rs);
+            const MvResult r = multiview_cost<NT, N1, GEN, false, U8>(c, x, y, cand, wt, rs);
             if (r.cost < cost_now) {
                 cost_now = r.cost; norm_now = cand; ratio_now = r.ratio; beview_now = r.beview; meta_dirty = true;
                 depth_now = cand_depth;  // only read by the refinement rounds
@@ -268,7 +261,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------
 // (3) multi-view matching cost for explicit (pixel, plane) pairs -- the unit the bench counts
 // ---------------------------------------------------------------------------------------------
-template <int NT, int MINB, int N1, bool GEN, bool PXF>
+template <int NT, int MINB, int N1, bool GEN, bool PXF, bool U8>
 __global__ void __launch_bounds__(NT, MINB) pm_eval_kernel(const __grid_constant__ PmConst c, const float *__restrict__ ref,
                                                      int n, const int2 *__restrict__ xy,
                                                      const float4 *__restrict__ planes, float *__restrict__ cost,
@@ -283,14 +276,14 @@ __global__ void __launch_bounds__(NT, MINB) pm_eval_kernel(const __grid_constant
     const int2 p = xy[i];
     float2 *wt = sm.wt + tid;
     const RefStats rs = window_weights<NT, N1>(c, ref, p.x, p.y, sm.sp, wt);
-    const MvResult r = multiview_cost<NT, N1, GEN, PXF>(c, p.x, p.y, planes[i], wt, rs);
+    const MvResult r = multiview_cost<NT, N1, GEN, PXF, U8>(c, p.x, p.y, planes[i], wt, rs);
     cost[i] = r.cost;
     beview[i] = r.beview;
     ratio[i] = r.ratio;
 }
 
 // cost of the planes currently stored (used by tsar_load_planes when no cost is supplied)
-template <int NT, int MINB, int N1, bool GEN>
+template <int NT, int MINB, int N1, bool GEN, bool U8>
 __global__ void __launch_bounds__(NT, MINB) pm_cost_of_state_kernel(const __grid_constant__ PmConst c,
                                                               const float *__restrict__ ref,
                                                               const float4 *__restrict__ plane,
@@ -305,7 +298,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_cost_of_state_kernel(const __grid
     float2 *wt = sm.wt + tid;
     const RefStats rs = window_weights<NT, N1>(c, ref, x, y, sm.sp, wt);
     const size_t p = (size_t)y * c.W + x;
-    cost[p] = multiview_cost<NT, N1, GEN>(c, x, y, plane[p], wt, rs).cost;
+    cost[p] = multiview_cost<NT, N1, GEN, false, U8>(c, x, y, plane[p], wt, rs).cost;
 }
 
 }  // namespace tsar

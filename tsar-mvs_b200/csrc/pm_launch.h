@@ -23,16 +23,16 @@ enum { PM_MODE_SP = 1, PM_MODE_PR = 2, PM_MODE_FUSED = 3 };
 
 struct PmVariant {
     const char *name;
-    cudaError_t (*init)(const PmConst &, const float *ref, const uint32_t *rng, int rng_len, float4 *plane,
+    // u8 != 0: sample the 8-bit copies of the source views (PmConst::tex8); bit-identical results
+    cudaError_t (*init)(int u8, const PmConst &, const float *ref, const uint32_t *rng, int rng_len, float4 *plane,
                         float *cost, cudaStream_t);
-    cudaError_t (*checker)(int mode, const PmConst &, const float *ref, const CheckerArgs &, cudaStream_t);
-    cudaError_t (*eval)(int wrapper_rounding, const PmConst &, const float *ref, int n, const int2 *xy, const float4 *planes, float *cost,
+    cudaError_t (*checker)(int u8, int mode, const PmConst &, const float *ref, const CheckerArgs &, cudaStream_t);
+    cudaError_t (*eval)(int u8, int wrapper_rounding, const PmConst &, const float *ref, int n, const int2 *xy, const float4 *planes, float *cost,
                         int *beview, float *ratio, cudaStream_t);
-    cudaError_t (*cost_of_state)(const PmConst &, const float *ref, const float4 *plane, float *cost, cudaStream_t);
+    cudaError_t (*cost_of_state)(int u8, const PmConst &, const float *ref, const float4 *plane, float *cost, cudaStream_t);
 };
 
 extern const PmVariant pm_variant_w11;      // 11x11 window (hRad 5, 36 samples), n_best <= 2 / COMB_BEST_N
-extern const PmVariant pm_variant_w11b, pm_variant_w11c, pm_variant_w11d, pm_variant_w11e, pm_variant_w11f;  // experimental launch shapes (env TSAR_B200_W11_VARIANT)
 extern const PmVariant pm_variant_w19;      // 19x19 window (hRad 9, 100 samples), n_best <= 2 / COMB_BEST_N
 extern const PmVariant pm_variant_generic;  // any window, any combination (run-time loops)
 
