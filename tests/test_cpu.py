@@ -228,3 +228,34 @@ def test_bench_reference_arm_contract():
     (metric, unit, higher_is_better) must be identical strings in both arms."""
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert src.count('"metric": "depthmaps/s"') == 2 and src.count('"higher_is_better": True') == 2
+
+
+def test_abi_layout_matches_reference(tmp_path):
+    """include/tsar_gipuma_abi.h against the reference's own headers: every field offset and size, compiled side by
+    side (only where the reference checkout exists; the GPU box does not have it)."""
+    ref = os.environ.get("TSAR_REFERENCE_DIR", "/root/reference")
+    if not os.path.exists(os.path.join(ref, "globalstate.h")):
+        pytest.skip("reference checkout not present")
+    fields = {
+        "Camera_cu": "P P_col34 P_inv M_inv R R_orig R_orig_inv t4 C4 fx fy f alpha baseline reference depthMin depthMax id K K_inv",
+        "CameraParameters_cu": "f rectified cameras idRef cols rows viewSelectionSubset viewSelectionSubsetNumber",
+        "LineState": "norm4 c depth fakedepth resize4 canny cenxi cenyi nein neip nump eacp ranp pind borlen depdif scale ransa "
+                     "text XYZ ratio beview lrdiff confid ranumax size n s l",
+        "AlgorithmParameters": "algorithm max_disparity min_disparity box_hsize box_vsize tau_color tau_gradient alpha gamma "
+                               "border_value iterations color_processing dispTol normTol census_epsilon self_similarity_n cam_scale "
+                               "num_img_processed costThresh good_factor n_best cost_comb viewSelection depthMin depthMax min_angle "
+                               "max_angle no_texture_sim no_texture_per max_views cols rows thres",
+        "GlobalState": "cameras lines cannylines cs params col row imgs cuArray",
+    }
+    src = ['#include "globalstate.h"', '#include "tsar_gipuma_abi.h"', "#include <cstddef>"]
+    for t, fs in fields.items():
+        src.append(f'static_assert(sizeof(::{t}) == sizeof(tsar_abi::{t}), "sizeof {t}");')
+        src.append(f'static_assert(alignof(::{t}) == alignof(tsar_abi::{t}), "alignof {t}");')
+        for f in fs.split():
+            src.append(f'static_assert(offsetof(::{t}, {f}) == offsetof(tsar_abi::{t}, {f}), "{t}::{f}");')
+    cu = tmp_path / "layout.cu"
+    cu.write_text("\n".join(src) + "\nint main(){return 0;}\n")
+    r = subprocess.run(["/usr/local/cuda/bin/nvcc", "-std=c++14", "-w", "-Wno-deprecated-gpu-targets", "-c", str(cu), "-o", str(tmp_path / "l.o"),
+                        "-I", os.path.join(ROOT, "oracle", "stubs"), "-I", ref, "-I", os.path.join(ROOT, "include")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
