@@ -39,8 +39,16 @@ if need "$OUT/libtsar_ref_snap.so" "$HERE/ref_driver.cu" "$REF/gipuma.cu" "$HERE
   # the two lines must be exactly the stores this recipe expects, otherwise fail loudly
   sed -n '1047p' "$REF/gipuma.cu" | grep -q 'gs.lines->c\[pindex\] = cost_now;'
   sed -n '1048p' "$REF/gipuma.cu" | grep -q 'gs.lines->norm4\[pindex\] = norm_now;'
+  # WMF / WMF_Final race the same way (a launch rewrites scale / depth / norm4 of pixels that other threads read
+  # as neighbours): their own-pixel accesses in the write-back blocks are redirected to scratch arrays too
+  sed -n '1691p' "$REF/gipuma.cu" | grep -q 'gs.lines->scale\[pindex\] = 1;'
+  sed -n '1470p' "$REF/gipuma.cu" | grep -q 'gs.lines->norm4\[pindex\] = norm_mid;'
   sed -e '1047s/gs\.lines->c\[pindex\]/gs.lines->ransa[pindex]/' \
       -e '1048s/gs\.lines->norm4\[pindex\]/gs.lines->resize4[pindex]/' \
+      -e '1686,1695s/gs\.lines->scale\[pindex\]/gs.lines->ransa[pindex]/' \
+      -e '1470,1485s/gs\.lines->norm4\[pindex\]/gs.lines->resize4[pindex]/g' \
+      -e '1470,1485s/gs\.lines->depth\[pindex\]/gs.lines->fakedepth[pindex]/g' \
+      -e '1470,1485s/gs\.lines->scale\[pindex\]/gs.lines->ransa[pindex]/g' \
       "$REF/gipuma.cu" > "$TMP/gipuma_snapshot.cu"
   $NVCC $COMMON -DORACLE_SNAPSHOT -I"$TMP" -I"$REF" "$HERE/ref_driver.cu" -o "$OUT/libtsar_ref_snap.so"
   rm -rf "$TMP"; trap - EXIT

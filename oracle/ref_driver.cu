@@ -18,7 +18,9 @@
 //         which the two final stores of gipuma_checkerboard_spatialProp_cu (gipuma.cu:1047-1048)
 //         go to lines->ransa / lines->resize4; the driver then copies them back for the launch's
 //         own colour.  This removes the same-colour read/write race and gives a
-//         deterministic oracle with Jacobi (pre-launch snapshot) semantics.
+//         deterministic oracle with Jacobi (pre-launch snapshot) semantics.  The same is done for the
+//         own-pixel write-back blocks of gipuma_WMF (gipuma.cu:1686-1695 -> ransa) and gipuma_WMF_Final
+//         (gipuma.cu:1470-1485 -> resize4 / fakedepth / ransa), which race on scale / depth / norm4.
 #include <cuda_runtime.h>
 #include <curand_kernel.h>
 #include <stdint.h>
@@ -340,16 +342,40 @@ PX_KERNEL(ref_compute_disp, gipuma_compute_disp)           // gipuma.cu:1848
 
 int ref_wmf(void *h, int iter) {  // gipuma.cu:1810
     RefCtx *r = (RefCtx *)h;
+    LineState *l = r->gs->lines;
+    const size_t n = (size_t)r->W * r->H;
+    (void)l; (void)n;
+#ifdef ORACLE_SNAPSHOT
+    RCHECK(cudaDeviceSynchronize());
+    RCHECK(cudaMemcpy(l->ransa, l->scale, n * 4, cudaMemcpyDefault));  // snapshot variant: results land in ransa
+#endif
     gipuma_WMF<float><<<r->grid_px, r->block_px>>>(*r->gs, iter);
     RCHECK(cudaGetLastError());
     RCHECK(cudaDeviceSynchronize());
+#ifdef ORACLE_SNAPSHOT
+    RCHECK(cudaMemcpy(l->scale, l->ransa, n * 4, cudaMemcpyDefault));
+#endif
     return 0;
 }
 int ref_wmf_final(void *h, int iter) {  // gipuma.cu:1845
     RefCtx *r = (RefCtx *)h;
+    LineState *l = r->gs->lines;
+    const size_t n = (size_t)r->W * r->H;
+    (void)l; (void)n;
+#ifdef ORACLE_SNAPSHOT
+    RCHECK(cudaDeviceSynchronize());  // snapshot variant: own-pixel results land in resize4 / fakedepth / ransa
+    RCHECK(cudaMemcpy(l->resize4, l->norm4, n * 16, cudaMemcpyDefault));
+    RCHECK(cudaMemcpy(l->fakedepth, l->depth, n * 4, cudaMemcpyDefault));
+    RCHECK(cudaMemcpy(l->ransa, l->scale, n * 4, cudaMemcpyDefault));
+#endif
     gipuma_WMF_Final<float><<<r->grid_px, r->block_px>>>(*r->gs, iter);
     RCHECK(cudaGetLastError());
     RCHECK(cudaDeviceSynchronize());
+#ifdef ORACLE_SNAPSHOT
+    RCHECK(cudaMemcpy(l->norm4, l->resize4, n * 16, cudaMemcpyDefault));
+    RCHECK(cudaMemcpy(l->depth, l->fakedepth, n * 4, cudaMemcpyDefault));
+    RCHECK(cudaMemcpy(l->scale, l->ransa, n * 4, cudaMemcpyDefault));
+#endif
     return 0;
 }
 

@@ -666,7 +666,9 @@ int tsar_wmf(tsar_ctx *ctx, int iter) {
     if (rc) return rc;
     if (iter < 0 || iter > 3) FAIL(TSAR_ERR_ARG, "WMF level must be 0..3 (gipuma.cu:1809)");
     if ((rc = consolidate(ctx))) return rc;
-    rc = wmf_launch(ctx->glue, ctx->tex[0], ctx->plane[0], ctx->depth, ctx->scale, iter, ctx->stream);
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    if ((rc = ensure_scratch(ctx, npx * 4))) return rc;
+    rc = wmf_launch(ctx->glue, ctx->ref_img, ctx->plane[0], ctx->depth, ctx->scale, (float *)ctx->scratch, iter, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     return rc;
@@ -678,8 +680,12 @@ int tsar_wmf_final(tsar_ctx *ctx, int iter) {
     if (iter < 0 || iter > 5) FAIL(TSAR_ERR_ARG, "WMF_Final level must be 0..5 (gipuma.cu:1844)");
     if (!ctx->region_text) FAIL(TSAR_ERR_STATE, "tsar_set_regions has not been called");
     if ((rc = consolidate(ctx))) return rc;
-    rc = wmf_final_launch(ctx->glue, ctx->tex[0], ctx->plane[0], ctx->depth, ctx->scale, ctx->canny, ctx->region_text,
-                          ctx->n_regions, iter, ctx->stream);
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    if ((rc = ensure_scratch(ctx, npx * 24))) return rc;
+    float4 *ps = (float4 *)ctx->scratch;
+    float *ds = (float *)((unsigned char *)ctx->scratch + npx * 16), *ss = ds + npx;
+    rc = wmf_final_launch(ctx->glue, ctx->ref_img, ctx->plane[0], ctx->depth, ctx->scale, ps, ds, ss, ctx->canny,
+                          ctx->region_text, ctx->n_regions, iter, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     return rc;
