@@ -147,6 +147,18 @@ int tsar_wmf_final(tsar_ctx *ctx, int iter);  /* gipuma_WMF_Final gipuma.cu:1295
  * 1722-1729).  Host pointers, n_regions entries. */
 int tsar_set_regions(tsar_ctx *ctx, int n_regions, const float *text, const float *norm4);
 
+/* Per-region plane fitting for textureless regions (the CPU RANSAC of main.cpp:1520-1730, calcLinePara
+ * main.cpp:147-164): for every region r with region_text[r] == -1, the reliable pixels (scale == 1) carrying label r
+ * in lines->canny are back-projected with lines->depth (a disparity) and a plane is fitted by 10 000 RANSAC triples
+ * with the reference's adaptive inlier threshold (seeded by region_size[r] = cannylines->size[r]) followed by
+ * 1000 x 4 local perturbation rounds.  rnd supplies the values the reference takes from rand():
+ * tsar_ransac_rand_per_region() (= 46 000) non-negative integers per region, region-major.  region_norm4
+ * (n_regions float4, host) is read for the initial value and receives (a, b, c, d) of the fitted regions;
+ * pass it to tsar_set_regions afterwards.  Uses the context's scale / canny / depth arrays. */
+int tsar_fit_region_planes(tsar_ctx *ctx, int n_regions, const float *region_text, const float *region_size,
+                           const uint32_t *rnd, float *region_norm4);
+int tsar_ransac_rand_per_region(void);
+
 /* ---- state transfer --------------------------------------------------------------------------- */
 int tsar_upload(tsar_ctx *ctx, int field, const void *host_src, size_t bytes);
 int tsar_download(tsar_ctx *ctx, int field, void *host_dst, size_t bytes);

@@ -94,3 +94,17 @@ class CpuOracle:
     def tex(self, img, x, y):
         img = np.ascontiguousarray(img, np.float32)
         return self.lib.oc_tex(img.ctypes.data, img.shape[1], img.shape[0], float(x), float(y))
+
+
+def fit_region_plane(camera_struct_type, cam0_struct, cam_f, depth, scale, canny, region, region_size, rnd, plane0):
+    """C restatement of the reference's per-region RANSAC (main.cpp:1520-1730) for one region."""
+    lib = C.CDLL(build())
+    lib.oc_fit_region_plane.argtypes = [C.c_int, C.c_int, C.POINTER(camera_struct_type), C.c_float, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    depth, scale, canny = (np.ascontiguousarray(a, np.float32) for a in (depth, scale, canny))
+    rnd = np.ascontiguousarray(rnd, np.uint32)
+    plane = np.ascontiguousarray(plane0, np.float32).copy()
+    H, W = depth.shape
+    used = lib.oc_fit_region_plane(W, H, C.byref(cam0_struct), float(cam_f), depth.ctypes.data, scale.ctypes.data,
+                                   canny.ctypes.data, int(region), float(region_size), rnd.ctypes.data, plane.ctypes.data)
+    return plane, used

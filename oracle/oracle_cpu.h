@@ -23,4 +23,6 @@ void oc_spatial(oc_ctx *c, int colour);
 void oc_refine(oc_ctx *c, int colour, uint64_t seed);
 void oc_iterate(oc_ctx *c, int iters, uint64_t seed0);
 void oc_output(oc_ctx *c, float *out);
+int oc_fit_region_plane(int W, int H, const tsar_camera *cam0, float cam_f, const float *depth, const float *scale,
+                        const float *canny, int region, float region_size, const uint32_t *rnd, float *plane_io);
 #endif

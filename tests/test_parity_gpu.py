@@ -358,3 +358,44 @@ def test_wmf_and_wmf_final_bit_exact(env, small):
     print(f"[wmf_final] worst per-level mismatch {worst:.5%}")
     assert (ref.download(rb.F_SCALE) != before).mean() > 0.001   # pixels were filled
     mine.close(); ref.close()
+
+
+def test_region_plane_fit_matches_restatement(env, small):
+    """Per-region RANSAC plane fit (main.cpp:1520-1730) -- the reference's host program cannot be built here (OpenCV,
+    Windows), so the checker is the scalar C restatement (oracle/oracle_cpu.c) fed with the same random stream;
+    both sides are IEEE double without contraction: bit-exact bar.  Also checks the fit is geometrically right."""
+    pkg, rb = env
+    L = pkg._lib
+    from oracle import cpu_binding as cb
+    from tsar_mvs_b200.engine import cameras_to_struct
+    scene = small
+    params, mine, _ = pc.make_engines(pkg, scene, variants=())
+    H, W = scene["H"], scene["W"]
+    rng = np.random.RandomState(9)
+    # disparities of the true surface + noise + 20 % gross outliers; every second pixel "reliable"
+    disp = (scene["cam_f"] / scene["gt_depth"]).astype(np.float32)
+    disp *= (1 + 0.0005 * rng.normal(size=disp.shape)).astype(np.float32)
+    out = rng.rand(H, W) < 0.2
+    disp[out] *= rng.uniform(0.8, 1.2, out.sum()).astype(np.float32)
+    scale = (rng.rand(H, W) < 0.5).astype(np.float32)
+    text = scene["region_text"].copy()
+    text[1] = -1.0                                         # a second region to fit, besides the textureless facet
+    size = np.array([(scene["labels"] == r).sum() / 16.0 for r in range(len(text))], np.float32)
+    per = mine.lib.tsar_ransac_rand_per_region()
+    rnd = rng.randint(0, 2 ** 31 - 1, size=(len(text), per)).astype(np.uint32)
+    mine.upload(L.F_DEPTH, disp); mine.upload(L.F_SCALE, scale); mine.upload(L.F_CANNY, scene["canny"])
+    p0 = np.tile(np.array([0, 0, 1, -1], np.float32), (len(text), 1))
+    fitted = mine.fit_region_planes(text, size, rnd, p0)
+    cams = cameras_to_struct(scene["cams"])
+    for r in range(len(text)):
+        if text[r] != -1:
+            assert np.array_equal(fitted[r], p0[r])
+            continue
+        want, used = cb.fit_region_plane(pkg._lib.TsarCamera, cams[0], scene["cam_f"], disp, scale, scene["canny"], r, size[r], rnd[r], p0[r])
+        assert used > 1000
+        assert pc.frac_bit_exact(fitted[r], want) == 1.0, (r, fitted[r], want)
+        # the fitted plane is the facet's true plane (n.X + d = 0 in the reference frame), up to sign
+        true = scene["region_norm4"][r].astype(np.float64)   # generator planes carry a small perturbation
+        cosang = abs(np.dot(fitted[r][:3], true[:3]) / np.linalg.norm(fitted[r][:3]) / np.linalg.norm(true[:3]))
+        assert cosang > np.cos(np.radians(8.0)), (r, fitted[r], true)
+    mine.close()

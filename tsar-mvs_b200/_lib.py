@@ -50,7 +50,7 @@ EXPORTS = [
     "tsar_create", "tsar_destroy", "tsar_last_error", "tsar_sync", "tsar_set_views", "tsar_set_params",
     "tsar_init_planes", "tsar_load_planes", "tsar_launch", "tsar_iterate", "tsar_eval_planes", "tsar_lrdiff",
     "tsar_getview", "tsar_get_disp", "tsar_update_scale_2", "tsar_update_scale", "tsar_compute_disp", "tsar_wmf",
-    "tsar_wmf_final", "tsar_set_regions", "tsar_upload", "tsar_download", "tsar_device_ptr", "tsar_depthmap",
+    "tsar_wmf_final", "tsar_set_regions", "tsar_fit_region_planes", "tsar_ransac_rand_per_region", "tsar_upload", "tsar_download", "tsar_device_ptr", "tsar_depthmap",
     "tsar_depthmap_host", "tsar_slic", "tsar_launch_count", "tsar_eval_count", "tsar_version", "tsar_dbg_tex_sample", "tsar_dbg_peaks", "tsar_dbg_eval_rounding", "tsar_dbg_tex_formats", "tsar_profile", "tsar_profile_read",
 ]
 
@@ -90,6 +90,8 @@ def load():
         "tsar_update_scale_2": (i, [vp]), "tsar_update_scale": (i, [vp]), "tsar_compute_disp": (i, [vp]),
         "tsar_wmf": (i, [vp, i]), "tsar_wmf_final": (i, [vp, i]),
         "tsar_set_regions": (i, [vp, i, vp, vp]),
+        "tsar_fit_region_planes": (i, [vp, i, vp, vp, vp, vp]),
+        "tsar_ransac_rand_per_region": (i, []),
         "tsar_upload": (i, [vp, i, vp, C.c_size_t]),
         "tsar_download": (i, [vp, i, vp, C.c_size_t]),
         "tsar_device_ptr": (i, [vp, i, C.POINTER(vp)]),

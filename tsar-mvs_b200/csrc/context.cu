@@ -18,6 +18,7 @@
 #include "debug_kernels.cuh"
 #include "glue_kernels.cuh"
 #include "pm_launch.h"
+#include "ransac_kernels.cuh"
 #include "slic_kernels.cuh"
 #include "wmf_kernels.cuh"
 
@@ -704,6 +705,65 @@ int tsar_set_regions(tsar_ctx *ctx, int n_regions, const float *text, const floa
     ctx->n_regions = n_regions;
     return TSAR_OK;
 }
+
+int tsar_fit_region_planes(tsar_ctx *ctx, int n_regions, const float *region_text, const float *region_size,
+                           const uint32_t *rnd, float *region_norm4) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (n_regions < 1 || !region_text || !region_size || !rnd || !region_norm4) FAIL(TSAR_ERR_ARG, "bad region arguments");
+    std::vector<int> targets;
+    for (int r = 0; r < n_regions; r++)
+        if (region_text[r] == -1.0f) targets.push_back(r);
+    if (targets.empty()) return TSAR_OK;
+    const int n = ctx->W * ctx->H, nb = (n + 1023) / 1024, nt = (int)targets.size();
+    int *d_counts = nullptr, *d_list = nullptr, *d_total = nullptr;
+    float3 *d_pts = nullptr;
+    uint32_t *d_rnd = nullptr;
+    RansacJob *d_jobs = nullptr;
+    float4 *d_out = nullptr;
+    std::vector<RansacJob> jobs(nt);
+    auto cleanup = [&]() { cudaFree(d_counts); cudaFree(d_list); cudaFree(d_total); cudaFree(d_pts); cudaFree(d_rnd); cudaFree(d_jobs); cudaFree(d_out); };
+#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); ctx->err = std::string(#call ": ") + cudaGetErrorString(e_); return TSAR_ERR_CUDA; } } while (0)
+    CKF(cudaMalloc(&d_counts, (size_t)nb * 4)); CKF(cudaMalloc(&d_list, (size_t)n * 4)); CKF(cudaMalloc(&d_total, 4));
+    CKF(cudaMalloc(&d_pts, (size_t)nt * kRansacMaxPts * sizeof(float3)));
+    CKF(cudaMalloc(&d_rnd, (size_t)nt * kRansacRandPerRegion * 4));
+    CKF(cudaMalloc(&d_jobs, (size_t)nt * sizeof(RansacJob))); CKF(cudaMalloc(&d_out, (size_t)nt * sizeof(float4)));
+    for (int t = 0; t < nt; t++) {
+        const int r = targets[t];
+        ransac_flag_kernel<<<nb, 1024, 0, ctx->stream>>>(ctx->scale, ctx->canny, n, r, d_counts);
+        ransac_scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(d_counts, nb, d_total);
+        ransac_scatter_kernel<<<nb, 1024, 0, ctx->stream>>>(ctx->scale, ctx->canny, n, r, d_counts, d_list);
+        int total = 0;
+        CKF(cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CKF(cudaStreamSynchronize(ctx->stream));
+        const int used = std::min(total, kRansacMaxPts);
+        float3 *pts = d_pts + (size_t)t * kRansacMaxPts;
+        if (used > 0) ransac_points_kernel<<<(used + 255) / 256, 256, 0, ctx->stream>>>(ctx->glue, ctx->depth, d_list, total, used, pts);
+        ctx->launches += 4;
+        jobs[t].pts = pts; jobs[t].n = used; jobs[t].size = region_size[r];
+        jobs[t].rnd = d_rnd + (size_t)t * kRansacRandPerRegion; jobs[t].out = d_out + t;
+        CKF(cudaMemcpyAsync(d_rnd + (size_t)t * kRansacRandPerRegion, rnd + (size_t)r * kRansacRandPerRegion,
+                            (size_t)kRansacRandPerRegion * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    std::vector<float4> out(nt);
+    for (int t = 0; t < nt; t++) out[t] = make_float4(region_norm4[4 * targets[t]], region_norm4[4 * targets[t] + 1], region_norm4[4 * targets[t] + 2], region_norm4[4 * targets[t] + 3]);
+    CKF(cudaMemcpyAsync(d_out, out.data(), (size_t)nt * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CKF(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nt * sizeof(RansacJob), cudaMemcpyHostToDevice, ctx->stream));
+    ransac_fit_kernel<<<nt, 1024, 0, ctx->stream>>>(d_jobs);
+    ctx->launches++;
+    CKF(cudaGetLastError());
+    CKF(cudaMemcpyAsync(out.data(), d_out, (size_t)nt * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CKF(cudaStreamSynchronize(ctx->stream));
+#undef CKF
+    for (int t = 0; t < nt; t++) {
+        float *o = region_norm4 + 4 * targets[t];
+        o[0] = out[t].x; o[1] = out[t].y; o[2] = out[t].z; o[3] = out[t].w;
+    }
+    cleanup();
+    return TSAR_OK;
+}
+
+int tsar_ransac_rand_per_region(void) { return kRansacRandPerRegion; }
 
 static void *field_ptr(tsar_ctx *ctx, int field, size_t *elt, size_t *count) {
     *count = (size_t)ctx->W * ctx->H;

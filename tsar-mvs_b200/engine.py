@@ -101,6 +101,18 @@ class DepthmapEngine:
         norm4 = np.ascontiguousarray(norm4, np.float32).reshape(-1, 4)
         self._ck(self.lib.tsar_set_regions(self.h, len(text), text.ctypes.data, norm4.ctypes.data), "tsar_set_regions")
 
+    def fit_region_planes(self, region_text, region_size, rnd, region_norm4):
+        """Per-region RANSAC plane fit (main.cpp:1520-1730) for regions with text == -1; rnd: [n_regions][46000]
+        uint32 (the values rand() would return).  Returns the updated [n_regions][4] planes."""
+        text = np.ascontiguousarray(region_text, np.float32)
+        size = np.ascontiguousarray(region_size, np.float32)
+        per = self.lib.tsar_ransac_rand_per_region()
+        rnd = np.ascontiguousarray(rnd, np.uint32).reshape(len(text), per)
+        planes = np.ascontiguousarray(region_norm4, np.float32).reshape(len(text), 4).copy()
+        self._ck(self.lib.tsar_fit_region_planes(self.h, len(text), text.ctypes.data, size.ctypes.data, rnd.ctypes.data,
+                                                 planes.ctypes.data), "tsar_fit_region_planes")
+        return planes
+
     # -- PatchMatch path ---------------------------------------------------------------------------
     def init_planes(self, seed):                      # gipuma_init_cu2
         self._ck(self.lib.tsar_init_planes(self.h, int(seed)), "tsar_init_planes")
