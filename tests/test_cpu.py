@@ -259,3 +259,35 @@ def test_abi_layout_matches_reference(tmp_path):
                         "-I", os.path.join(ROOT, "oracle", "stubs"), "-I", ref, "-I", os.path.join(ROOT, "include")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_cli_flag_parsing_matches_run_scripts(pkg):
+    """The command line the reference's scripts build (scripts/pipes.sh:45), incl. its empty and unknown flags."""
+    from tsar_mvs_b200 import cli
+    argv = ("00000003.jpg 00000000.jpg 00000001.jpg -mslp_folder ./data/TRAIN/pipes/ -images_folder data/TRAIN/pipes/images/ "
+            "-krt_file data/x.txt -output_folder results/pipes/ -no_display --cam_scale=1 --iterations=8 --blocksize=11 "
+            "--cost_gamma=10 --cost_comb=best_n --n_best=1 --min_angle= --max_angle= --bogus=3").split()
+    o = cli.parse_args(argv)
+    assert o["images"] == ["00000003.jpg", "00000000.jpg", "00000001.jpg"]
+    assert (o["blocksize"], o["iterations"], o["n_best"], o["cost_comb"], o["cam_scale"]) == (11, 8, 1, 1, 1.0)
+    assert o["mslp_folder"] == "./data/TRAIN/pipes/" and o["no_display"] is True
+
+
+def test_dataset_readers_roundtrip(tmp_path, pkg, tiny):
+    """cams/<id>_cam.txt and pair.txt as the reference reads them (fileIoUtils.h:111-163, main.cpp:1351-1376)."""
+    from tsar_mvs_b200 import cli, scene
+    sc, names = cli.write_synthetic_dataset("tiny", str(tmp_path))
+    Ks, Rs, ts = [], [], []
+    for n in names:
+        K, R, t, dmin, dmax = cli.read_cam_txt(str(tmp_path / "cams" / f"{n[:8]}_cam.txt"))
+        Ks.append(K); Rs.append(R); ts.append(t)
+    cams = scene.cameras_from_krt(Ks, Rs, ts, dmin, dmax)
+    for a, b in zip(cams, tiny["cams"]):
+        for k in ("K", "R", "t4", "M_inv", "C4", "P_col34", "R_orig"):
+            assert np.array_equal(np.asarray(a[k], np.float32), np.asarray(b[k], np.float32)), k
+    # reference view = image 2: the list is [2, 0, 1, 3]; pair.txt lists neighbours 0, 1, 3 -> list positions 1, 2, 3
+    assert cli.read_pair_subset(str(tmp_path / "pair.txt"), 2) == [1, 2, 3]
+    assert cli.read_pair_subset(str(tmp_path / "pair.txt"), 0) == [1, 2, 3]
+    import cv2
+    im = cv2.imread(str(tmp_path / "images" / names[1]), cv2.IMREAD_GRAYSCALE)
+    assert np.array_equal(im.astype(np.float32), tiny["images"][1])

@@ -6,6 +6,8 @@ Bar: bit-exact against the snapshot build (integer/float bits identical); agains
 we report agreement next to the build's own run-to-run noise floor and require ours to be no further
 from it than the snapshot build is.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -453,3 +455,29 @@ def test_full_size_properties(env, monkeypatch):
     assert 6.6e9 < n_ev < 6.8e9                                             # 6.67 G pmCost evaluations per depthmap
     del imgs
     torch.cuda.empty_cache()
+
+
+def test_cli_end_to_end_on_synthetic_dataset(env, tmp_path):
+    """tsar_cli.py with the reference's flags on a dataset in the reference's folder layout: writes TSAR_disp.dmb /
+    TSAR_normals.dmb (fileIoUtils.h:333-381) identical to driving the engine directly."""
+    import subprocess
+    import sys
+    pkg, rb = env
+    L = pkg._lib
+    root = str(tmp_path / "ds") + "/"
+    cmd = [sys.executable, os.path.join(pc.ROOT, "tsar_cli.py"), "--synthetic=tiny", "-mslp_folder", root, "-krt_file", "x",
+           "-no_display", "--cam_scale=1", "--iterations=3", "--blocksize=11", "--cost_comb=best_n", "--n_best=1",
+           "--min_angle=", "--max_angle=", f"--seed={SEED}"]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=pc.ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    from tsar_mvs_b200 import dmb
+    depth = dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_disp.dmb"))
+    normal = dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_normals.dmb"))
+    scene = pkg.scene.make_scene("tiny")
+    params, mine, _ = pc.make_engines(pkg, scene, iterations=3, variants=())
+    mine.depthmap(SEED)
+    out = mine.download(L.F_NORM4)
+    mine.close()
+    assert depth.shape == (scene["H"], scene["W"]) and normal.shape == (scene["H"], scene["W"], 3)
+    assert pc.frac_bit_exact(depth, out[..., 3]) == 1.0
+    assert pc.frac_bit_exact(normal, np.ascontiguousarray(out[..., :3])) == 1.0

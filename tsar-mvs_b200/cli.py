@@ -1,0 +1,223 @@
+"""Command line of the reference (`gipuma <ref image> <other images...> flags`, main.cpp:708-1009, run scripts
+scripts/*.sh) on top of libtsar_b200.so.
+
+    python -m tsar_cli 00000000.jpg 00000001.jpg ... -mslp_folder data/TRAIN/pipes/ -images_folder data/TRAIN/pipes/images/ \
+        -krt_file x -output_folder results/pipes/ -no_display --cam_scale=1 --iterations=8 --blocksize=11 \
+        --cost_gamma=10 --cost_comb=best_n --n_best=1 --min_angle= --max_angle=
+
+Kept from the reference: positional arguments are image names, the first one is the reference view; `--key=value`
+numeric flags, `-key value` path flags, `-color_processing` / `-view_selection` booleans; unknown flags only warn
+(main.cpp:941-945) -- the scripts pass an unknown `-no_display` and empty `--min_angle=`/`--max_angle=`;
+`-krt_file` merely selects the MVSNet-style reader, its value is ignored (fileIoUtils.h:111-118); cameras come from
+`<mslp>/cams/<8-digit stem>_cam.txt`, the source views from `<mslp>/pair.txt` (main.cpp:1351-1376, camera id =
+atoi(name[4:8])); results go to `<mslp>/APD/<stem>/TSAR_disp.dmb` and `TSAR_normals.dmb` (main.cpp:1807-1861).
+
+Flows:
+  * default (north-star): random initialisation + red/black PatchMatch + L/R check + confidence + output layout;
+  * `-import_apd`: the shipped flow -- planes imported from `<mslp>/APD/<stem>/depths_geom.dmb` + `normals.dmb`
+    (main.cpp:1459-1490) then gipuma_get_disp / getview / output.
+Textureless-region completion needs the weak-texture detector of main.cpp:365-596 (OpenCV HoughLinesP; SURVEY row
+f3, not built): pass a precomputed label map with `-regions_file labels.npy` (+ `-regions_text text.npy`) to enable
+plane fitting (tsar_fit_region_planes) and depth completion.
+Extra: `--synthetic=<C1|C2|small|tiny>` first writes a synthetic dataset in the reference's folder layout.
+"""
+import os
+import sys
+
+import numpy as np
+
+from . import dmb, scene
+from .engine import DepthmapEngine, make_params
+
+NUMERIC = {"blocksize", "iterations", "n_best", "cost_gamma", "depth_min", "depth_max", "max_views", "min_angle", "max_angle",
+           "cam_scale", "cost_tau_color", "cost_tau_gradient", "cost_alpha", "disp_tol", "normal_tol", "census_epsilon",
+           "self_similarity_n", "good_factor", "num_img_processed", "seed", "synthetic", "device"}
+PATHS = {"images_folder", "mslp_folder", "krt_file", "output_folder", "p_folder", "camera_folder", "calib_file", "pmvs_folder",
+         "bounding_folder", "regions_file", "regions_text", "regions_size"}
+BOOLS = {"color_processing", "view_selection", "import_apd", "no_display"}
+
+
+def parse_args(argv):
+    """getParametersFromCommandLine (main.cpp:708-1009), tolerant in the same places."""
+    opt = dict(images=[], blocksize=19, iterations=8, n_best=2, cost_comb=1, cam_scale=1.0, depth_min=-1.0, depth_max=-1.0,
+               seed=20240601, device=0, images_folder="", mslp_folder="", output_folder="", synthetic=None,
+               color_processing=False, import_apd=False, regions_file=None, regions_text=None, regions_size=None)
+    i = 0
+    while i < len(argv):
+        a = argv[i]
+        if a.startswith("--"):
+            key, _, val = a[2:].partition("=")
+            if key == "cost_comb":
+                opt["cost_comb"] = {"all": 0, "best_n": 1, "angle": 2, "good": 3}.get(val, opt["cost_comb"])
+            elif key == "synthetic":
+                opt["synthetic"] = val
+            elif key in NUMERIC:
+                if val != "":  # the scripts pass `--min_angle=` with an empty value
+                    opt[key] = float(val) if "." in val or key in ("cam_scale", "depth_min", "depth_max") else int(val)
+            else:
+                print(f"[tsar_cli] warning: unknown option {a}", file=sys.stderr)
+        elif a.startswith("-") and len(a) > 1 and not a[1].isdigit():
+            key = a[1:]
+            if key in BOOLS:
+                opt[key] = True
+            elif key in PATHS:
+                i += 1
+                opt[key] = argv[i] if i < len(argv) else ""
+            else:
+                print(f"[tsar_cli] warning: unknown option {a}", file=sys.stderr)
+        else:
+            opt["images"].append(a)
+        i += 1
+    return opt
+
+
+# ---- dataset I/O -------------------------------------------------------------------------------------------
+def read_cam_txt(path):
+    """MVSNet-style camera file as readKRtFileMiddlebury reads it (fileIoUtils.h:111-163): 'extrinsic', 4x4 [R|t],
+    'intrinsic', 3x3 K, then depth_min interval depth_num depth_max."""
+    tok = open(path).read().split()
+    assert tok[0] == "extrinsic", path
+    E = np.array(tok[1:17], float).reshape(4, 4)
+    assert tok[17] == "intrinsic", path
+    K = np.array(tok[18:27], float).reshape(3, 3)
+    tail = [float(v) for v in tok[27:31]]
+    depth_min, depth_max = tail[0], tail[3]
+    return K, E[:3, :3], E[:3, 3], depth_min, depth_max
+
+
+def write_cam_txt(path, K, R, t, depth_min, depth_max, interval=0.0, depth_num=0):
+    E = np.eye(4)
+    E[:3, :3], E[:3, 3] = R, t
+    with open(path, "w") as f:
+        f.write("extrinsic\n" + "\n".join(" ".join(repr(float(v)) for v in row) for row in E) + "\n\nintrinsic\n")
+        f.write("\n".join(" ".join(repr(float(v)) for v in row) for row in np.asarray(K, float)) + "\n\n")
+        f.write(f"{depth_min!r} {interval!r} {depth_num} {depth_max!r}\n")
+
+
+def read_pair_subset(path, camera_id):
+    """Source views of camera `camera_id` as indices into the command-line image list (main.cpp:1351-1376): the list is
+    [reference, all other images in order], so image k maps to k+1 if k < camera_id else k."""
+    lines = open(path).read().split("\n")
+    line = lines[2 * camera_id + 2].split()  # 1 header line, then per camera: id line + neighbour line
+    n = int(line[0])
+    subset = []
+    for j in range(n):
+        k = int(line[1 + 2 * j])
+        subset.append(k if k > camera_id else k + 1)
+    return subset
+
+
+def write_pair_txt(path, neighbours):
+    with open(path, "w") as f:
+        f.write(f"{len(neighbours)}\n")
+        for i, nb in enumerate(neighbours):
+            f.write(f"{i}\n{len(nb)} " + " ".join(f"{k} 1.0" for k in nb) + "\n")
+
+
+def _imread_gray(path):
+    if path.endswith(".npy"):
+        return np.load(path).astype(np.float32)
+    import cv2  # image decoding only (the reference uses cv::imread, main.cpp:1302)
+    im = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+    if im is None:
+        raise FileNotFoundError(path)
+    return im.astype(np.float32)
+
+
+def write_synthetic_dataset(cfg_name, root):
+    """Writes a synthetic scene in the reference's folder layout: <root>/images/%08d.png, <root>/cams/%08d_cam.txt,
+    <root>/pair.txt.  Returns (scene dict, list of image names)."""
+    import cv2
+    sc = scene.make_scene(cfg_name)
+    os.makedirs(os.path.join(root, "images"), exist_ok=True)
+    os.makedirs(os.path.join(root, "cams"), exist_ok=True)
+    names = []
+    n = len(sc["images"])
+    for i, (im, cam) in enumerate(zip(sc["images"], sc["cams"])):
+        name = f"{i:08d}.png"
+        cv2.imwrite(os.path.join(root, "images", name), im.astype(np.uint8))
+        R, C = cam["_R_world"], cam["_C_world"]
+        write_cam_txt(os.path.join(root, "cams", f"{i:08d}_cam.txt"), cam["K"], R, -R @ C, cam["depthMin"], cam["depthMax"])
+        names.append(name)
+    write_pair_txt(os.path.join(root, "pair.txt"), [[k for k in range(n) if k != i] for i in range(n)])
+    return sc, names
+
+
+# ---- the driver ---------------------------------------------------------------------------------------------
+def run(argv):
+    opt = parse_args(argv)
+    mslp = opt["mslp_folder"]
+    if opt["synthetic"]:
+        mslp = mslp or "./synthetic_" + opt["synthetic"] + "/"
+        _, names = write_synthetic_dataset(opt["synthetic"], mslp)
+        opt["images"] = opt["images"] or names
+        opt["images_folder"] = os.path.join(mslp, "images/")
+    if not opt["images"]:
+        print(__doc__)
+        return 2
+    names = opt["images"]
+    stem = names[0][:8]                         # main.cpp:1462: numind = imgname.substr(0, 8)
+    camera_id = int(names[0][4:8])              # main.cpp:1347-1349: atoi(name.substr(4, 8)) (sic: 4 characters)
+    images = [_imread_gray(os.path.join(opt["images_folder"], n)) for n in names]
+    Ks, Rs, ts, dmin, dmax = [], [], [], None, None
+    for i, n in enumerate(names):
+        K, R, t, a, b = read_cam_txt(os.path.join(mslp, "cams", f"{n[:8]}_cam.txt"))
+        K = K.copy()
+        K[:2] /= opt["cam_scale"]               # scaleK (cameraGeometryUtils.h:141-151)
+        Ks.append(K); Rs.append(R); ts.append(t)
+        if i == 0:
+            dmin, dmax = a, b                   # depth range of the reference view (fileIoUtils.h:145-153)
+    if opt["depth_min"] > 0:
+        dmin = opt["depth_min"]
+    if opt["depth_max"] > 0:
+        dmax = opt["depth_max"]
+    cams = scene.cameras_from_krt(Ks, Rs, ts, dmin, dmax)
+    subset = read_pair_subset(os.path.join(mslp, "pair.txt"), camera_id)
+    subset = [s for s in subset if s < len(names)]
+    f = float(np.float32(cams[0]["f"]))
+    params = make_params(box=opt["blocksize"], iterations=opt["iterations"], n_best=opt["n_best"], cost_comb=opt["cost_comb"],
+                         min_disparity=float(np.float32(f / np.float32(dmax))), max_disparity=float(np.float32(f / np.float32(dmin))))
+    eng = DepthmapEngine(int(opt["device"]))
+    eng.set_views(images, cams, subset, cam_f=f)
+    eng.set_params(params)
+    from . import _lib as L
+    out_dir = os.path.join(mslp, "APD", stem)
+    H, W = images[0].shape
+    if opt["import_apd"]:                       # shipped flow, main.cpp:1459-1490
+        depth = dmb.read_dmb(os.path.join(out_dir, "depths_geom.dmb"))
+        normal = dmb.read_dmb(os.path.join(out_dir, "normals.dmb"))
+        n4 = np.concatenate([normal, np.zeros((H, W, 1), np.float32)], axis=-1)
+        eng.upload(L.F_NORM4, n4)
+        eng.upload(L.F_COST, np.ones((H, W), np.float32))
+        eng.upload(L.F_DEPTH, (np.float32(f) / depth).astype(np.float32))
+        eng.get_disp()
+    else:
+        eng.init_planes(int(opt["seed"]))
+        eng.iterate(opt["iterations"], int(opt["seed"]))
+        eng.lrdiff()
+    eng.getview()
+    confid = eng.download(L.F_CONFID)
+    if opt["regions_file"]:
+        labels = np.load(opt["regions_file"]).astype(np.float32)
+        text = np.load(opt["regions_text"]).astype(np.float32)
+        size = np.load(opt["regions_size"]).astype(np.float32) if opt["regions_size"] else \
+            np.array([(labels == r).sum() / 16.0 for r in range(len(text))], np.float32)
+        eng.upload(L.F_CANNY, labels)
+        eng.upload(L.F_SCALE, (confid > 0.8).astype(np.float32))       # reliable pixels (stands in for APD's weak.png)
+        rng = np.random.RandomState(int(opt["seed"]) & 0x7fffffff)
+        rnd = rng.randint(0, 2 ** 31 - 1, size=(len(text), eng.lib.tsar_ransac_rand_per_region())).astype(np.uint32)
+        planes = eng.fit_region_planes(text, size, rnd, np.tile(np.array([0, 0, 1, -1], np.float32), (len(text), 1)))
+        eng.set_regions(text, planes)
+        eng.update_scale_2()
+        eng.update_scale()
+    eng.compute_disp()
+    out = eng.download(L.F_NORM4)
+    dmb.write_outputs(out_dir, out)
+    dmb.write_dmb(os.path.join(out_dir, "TSAR_confidence.dmb"), confid)   # computed but never written by the reference
+    print(f"[tsar_cli] {stem}: {W}x{H}, {len(subset)} source views -> {out_dir}/TSAR_disp.dmb, TSAR_normals.dmb")
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(run(sys.argv[1:]))

@@ -31,6 +31,26 @@ def _look_at(C, target):
     return np.stack([x, y, z])  # rows: world -> camera
 
 
+def cameras_from_krt(Ks, Rs, ts, depth_min, depth_max):
+    """Camera_cu fields as getCameraParameters(transformP=true) fills them (cameraGeometryUtils.h:174-364)
+    from per-image K, world->camera R and t; image 0 is the reference.  Note the reference's choices that are kept:
+    every P uses the intrinsics of camera 0, baseline is hard-coded to 1, fx/fy/f/alpha come from K_0."""
+    Ks = [np.asarray(K, float) for K in Ks]
+    Rs = [np.asarray(R, float) for R in Rs]
+    ts = [np.asarray(t, float).reshape(3) for t in ts]
+    R0, t0, K0 = Rs[0], ts[0], Ks[0]
+    cams = []
+    for K, R, t in zip(Ks, Rs, ts):
+        Rp = R @ R0.T                          # cameraGeometryUtils.h:113-139
+        tp = t - Rp @ t0
+        P = K0 @ np.concatenate([Rp, tp[:, None]], axis=1)
+        cams.append(dict(
+            K=K, K_inv=np.linalg.inv(K), R=Rp, R_orig=R, R_orig_inv=np.linalg.inv(R), M_inv=np.linalg.inv(P[:, :3]),
+            t4=tp, P_col34=P[:, 3], C4=-Rp.T @ tp, fx=K0[0, 0], fy=K0[1, 1], f=K0[0, 0], alpha=K0[0, 0] / K0[1, 1],
+            baseline=1.0, depthMin=depth_min, depthMax=depth_max))
+    return cams
+
+
 def make_cameras(W, H, n_images, fx, radius, arc_deg, depth_range=(0.7, 1.45), ref_index=0):
     """Cameras on an arc, sorted by baseline from the middle one.  Camera `ref_index` of that list becomes
     the reference (index 0 of the returned list); the others keep their order."""
@@ -54,18 +74,9 @@ def make_cameras(W, H, n_images, fx, radius, arc_deg, depth_range=(0.7, 1.45), r
         ts.append(-R @ C)
     order = [ref_index % n_images] + [i for i in range(n_images) if i != ref_index % n_images]
     Rs, ts, Cs = [Rs[i] for i in order], [ts[i] for i in order], [Cs[i] for i in order]
-    R0, t0 = Rs[0], ts[0]
-    cams = []
-    for i in range(n_images):
-        Rp = Rs[i] @ R0.T                      # cameraGeometryUtils.h:113-139
-        tp = ts[i] - Rp @ t0
-        P = K @ np.concatenate([Rp, tp[:, None]], axis=1)
-        M = P[:, :3]
-        cams.append(dict(
-            K=K, K_inv=np.linalg.inv(K), R=Rp, R_orig=Rs[i], R_orig_inv=Rs[i].T, M_inv=np.linalg.inv(M),
-            t4=tp, P_col34=P[:, 3], C4=-Rp.T @ tp, fx=K[0, 0], fy=K[1, 1], f=K[0, 0], alpha=K[0, 0] / K[1, 1],
-            baseline=1.0, depthMin=depth_range[0] * radius, depthMax=depth_range[1] * radius,
-            _R_world=Rs[i], _C_world=Cs[i]))
+    cams = cameras_from_krt([K] * n_images, Rs, ts, depth_range[0] * radius, depth_range[1] * radius)
+    for c, R, C in zip(cams, Rs, Cs):
+        c["_R_world"], c["_C_world"] = R, C
     return cams
 
 
