@@ -349,6 +349,7 @@ int tsar_destroy(tsar_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     free_state(ctx);
     free_images(ctx);
+    for (auto &pr : ctx->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaFree(ctx->d_tex); cudaFree(ctx->d_cams); cudaFree(ctx->rng); cudaFree(ctx->scratch);
     cudaFree(ctx->region_text); cudaFree(ctx->region_plane); cudaFree(ctx->d_flag);
     slic_free(ctx->slic);
