@@ -128,6 +128,11 @@ int ref_create(int W, int H, int n_images, const float *const *images, const tsa
     r->gs = new GlobalState;  // managed, as main.cpp:1876
     r->params = new AlgorithmParameters;
     GlobalState &gs = *r->gs;
+    // LineState has no constructor: its pointer members hold whatever the managed block held before, and
+    // ~LineState cudaFree()s all of them.  The reference program builds one GlobalState per process and
+    // resize()s both states; a test process builds many, so start both from null pointers.
+    memset(gs.lines, 0, sizeof(LineState));
+    memset(gs.cannylines, 0, sizeof(LineState));
     AlgorithmParameters &ap = *r->params;
     ap.box_hsize = p->box_hsize;
     ap.box_vsize = p->box_vsize;
@@ -211,6 +216,7 @@ int ref_destroy(void *h) {
     delete r->gs;
     delete r->params;
     delete r;
+    cudaGetLastError();  // nothing from teardown may surface in the next engine's launch checks
     return 0;
 }
 

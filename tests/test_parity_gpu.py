@@ -114,6 +114,25 @@ def test_full_sequence_vs_reference(env, cfg, iters):
     assert ours["frac_ok"] == twin["frac_ok"] and ours["frac_depth_ok"] == twin["frac_depth_ok"]
 
 
+@pytest.mark.parametrize("box,n_best,cost_comb", [(19, 1, 1), (7, 3, 1), (9, 2, 0), (11, 2, 1), (5, 1, 1), (25, 1, 1), (12, 1, 1), (11, 3, 0)])
+def test_full_sequence_other_windows_and_view_combinations(env, box, n_best, cost_comb):
+    """The 19x19 kernel variant, the runtime-window variant (any other blocksize) and the n_best > 1 / cost_comb
+    paths of the propagation + refinement kernel, through the whole per-view sequence."""
+    pkg, rb = env
+    L = pkg._lib
+    scene = pkg.scene.make_scene("tiny")
+    params, mine, refs = pc.make_engines(pkg, scene, iterations=2, box=box, n_best=n_best, cost_comb=cost_comb, variants=("snapshot",))
+    snap = refs["snapshot"]
+    mine.depthmap(SEED); snap.depthmap(SEED, iters=2)
+    o_m, o_s = mine.download(L.F_NORM4), snap.download(rb.F_NORM4)
+    c_m, c_s = mine.download(L.F_COST), snap.download(rb.F_COST)
+    v_m, v_s = mine.download(L.F_BEVIEW), snap.download(rb.F_BEVIEW)
+    mine.close(); snap.close()
+    assert pc.frac_bit_exact(o_m, o_s) == 1.0
+    assert pc.frac_bit_exact(c_m, c_s) == 1.0
+    assert (v_m == v_s).all()
+
+
 def test_fused_equals_unfused(env, small, monkeypatch):
     """Fusing spatial propagation + refinement of one colour into one kernel changes nothing."""
     pkg, rb = env
