@@ -41,6 +41,9 @@ struct tsar_ctx {
     std::vector<cudaArray_t> arrays8;          // 8-bit copies of the views (sampling fast path)
     std::vector<cudaTextureObject_t> tex8;
     unsigned char *stage8 = nullptr;           // staging buffer for the float -> u8 conversion
+    int region_cap = 0;                        // allocated entries of region_text / region_plane
+    float *stage32 = nullptr;                  // linear landing buffer for host images (tsar_set_views, on_device = 0)
+    size_t stage32_n = 0;
     int *d_flag = nullptr;
     int use_u8 = 0;                            // every image is 8-bit valued: sample the 8-bit textures
     bool allow_u8 = true;                      // env TSAR_B200_NO_U8=1 switches the fast path off
@@ -351,7 +354,7 @@ int tsar_destroy(tsar_ctx *ctx) {
     free_images(ctx);
     for (auto &pr : ctx->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaFree(ctx->d_tex); cudaFree(ctx->d_cams); cudaFree(ctx->rng); cudaFree(ctx->scratch);
-    cudaFree(ctx->region_text); cudaFree(ctx->region_plane); cudaFree(ctx->d_flag);
+    cudaFree(ctx->region_text); cudaFree(ctx->region_plane); cudaFree(ctx->d_flag); cudaFree(ctx->stage32);
     slic_free(ctx->slic);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -410,55 +413,64 @@ int tsar_set_views(tsar_ctx *ctx, int W, int H, int n_images, const float *const
         CK(cudaMalloc(&ctx->d_cams, n_images * sizeof(CamDev)));
         CK(cudaMemcpyAsync(ctx->d_tex, ctx->tex.data(), n_images * sizeof(cudaTextureObject_t), cudaMemcpyHostToDevice, ctx->stream));
     }
-    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    for (int i = 0; i < n_images; i++)
-        CK(cudaMemcpy2DToArrayAsync(ctx->arrays[i], 0, 0, images[i], (size_t)W * 4, (size_t)W * 4, H, kind, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->ref_img, images[0], n * 4, kind, ctx->stream));
     // 8-bit copies: the reference's inputs are 8-bit grey images converted to float (main.cpp:1423), for which an
     // 8-bit texture gives bit-identical bilinear samples at a quarter of the texel traffic (pm_core.cuh, view_cost)
     ctx->use_u8 = 0;
-    if (ctx->allow_u8) {
-        if ((int)ctx->arrays8.size() != n_images) {
-            for (auto t : ctx->tex8) cudaDestroyTextureObject(t);
-            for (auto a : ctx->arrays8) cudaFreeArray(a);
-            ctx->tex8.clear(); ctx->arrays8.clear();
-            cudaFree(ctx->stage8); ctx->stage8 = nullptr;
-            cudaChannelFormatDesc c8 = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
-            for (int i = 0; i < n_images; i++) {
-                cudaArray_t a;
-                CK(cudaMallocArray(&a, &c8, W, H));
-                ctx->arrays8.push_back(a);
-                cudaResourceDesc rd;
-                memset(&rd, 0, sizeof(rd));
-                rd.resType = cudaResourceTypeArray;
-                rd.res.array.array = a;
-                cudaTextureDesc td;
-                memset(&td, 0, sizeof(td));
-                td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-                td.filterMode = cudaFilterModeLinear;
-                td.readMode = cudaReadModeNormalizedFloat;
-                td.normalizedCoords = 0;
-                cudaTextureObject_t t;
-                CK(cudaCreateTextureObject(&t, &rd, &td, NULL));
-                ctx->tex8.push_back(t);
-            }
-            CK(cudaMalloc(&ctx->stage8, n));
-            if (!ctx->d_flag) CK(cudaMalloc(&ctx->d_flag, sizeof(int)));
-        }
-        CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
-        float *lin = nullptr;  // linear device copy of view i (view 0 is already in ref_img)
-        if (!on_device) CK(cudaMalloc(&lin, n * 4));
+    if (ctx->allow_u8 && (int)ctx->arrays8.size() != n_images) {
+        for (auto t : ctx->tex8) cudaDestroyTextureObject(t);
+        for (auto a : ctx->arrays8) cudaFreeArray(a);
+        ctx->tex8.clear(); ctx->arrays8.clear();
+        cudaFree(ctx->stage8); ctx->stage8 = nullptr;
+        cudaChannelFormatDesc c8 = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
         for (int i = 0; i < n_images; i++) {
-            const float *src = on_device ? images[i] : lin;
-            if (!on_device) CK(cudaMemcpyAsync(lin, images[i], n * 4, cudaMemcpyHostToDevice, ctx->stream));
+            cudaArray_t a;
+            CK(cudaMallocArray(&a, &c8, W, H));
+            ctx->arrays8.push_back(a);
+            cudaResourceDesc rd;
+            memset(&rd, 0, sizeof(rd));
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = a;
+            cudaTextureDesc td;
+            memset(&td, 0, sizeof(td));
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModeLinear;
+            td.readMode = cudaReadModeNormalizedFloat;
+            td.normalizedCoords = 0;
+            cudaTextureObject_t t;
+            CK(cudaCreateTextureObject(&t, &rd, &td, NULL));
+            ctx->tex8.push_back(t);
+        }
+        CK(cudaMalloc(&ctx->stage8, n));
+    }
+    if (!ctx->d_flag) CK(cudaMalloc(&ctx->d_flag, sizeof(int)));
+    // host images cross the bus once, into a persistent linear staging buffer (no per-call cudaMalloc/cudaFree: those
+    // synchronise the whole device and would serialise contexts that pipeline views on other streams)
+    if (!on_device && ctx->stage32_n < n) {
+        cudaFree(ctx->stage32); ctx->stage32 = nullptr; ctx->stage32_n = 0;
+        CK(cudaMalloc(&ctx->stage32, n * 4));
+        ctx->stage32_n = n;
+    }
+    CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    for (int i = 0; i < n_images; i++) {
+        const float *src = images[i];
+        if (!on_device) {
+            float *dst = (i == 0) ? ctx->ref_img : ctx->stage32;   // view 0 is also kept linear (hoisted window terms)
+            CK(cudaMemcpyAsync(dst, images[i], n * 4, cudaMemcpyHostToDevice, ctx->stream));
+            src = dst;
+        } else if (i == 0) {
+            CK(cudaMemcpyAsync(ctx->ref_img, images[0], n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        CK(cudaMemcpy2DToArrayAsync(ctx->arrays[i], 0, 0, src, (size_t)W * 4, (size_t)W * 4, H, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (ctx->allow_u8) {
             to_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->stage8, n, ctx->d_flag);
             CK(cudaMemcpy2DToArrayAsync(ctx->arrays8[i], 0, 0, ctx->stage8, (size_t)W, (size_t)W, H, cudaMemcpyDeviceToDevice, ctx->stream));
             ctx->launches++;
         }
+    }
+    if (ctx->allow_u8) {
         int flag = 1;
         CK(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (lin) cudaFree(lin);
         ctx->use_u8 = (flag == 0);
     }
     ctx->W = W; ctx->H = H; ctx->n_images = n_images; ctx->V = V;
@@ -696,10 +708,13 @@ int tsar_wmf_final(tsar_ctx *ctx, int iter) {
 int tsar_set_regions(tsar_ctx *ctx, int n_regions, const float *text, const float *norm4) {
     if (!ctx || n_regions < 1 || !text || !norm4) return TSAR_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    cudaFree(ctx->region_text); cudaFree(ctx->region_plane);
-    ctx->region_text = nullptr; ctx->region_plane = nullptr;
-    CK(cudaMalloc(&ctx->region_text, (size_t)n_regions * 4));
-    CK(cudaMalloc(&ctx->region_plane, (size_t)n_regions * 16));
+    if (n_regions > ctx->region_cap) {  // grow only: cudaFree/cudaMalloc synchronise the device
+        cudaFree(ctx->region_text); cudaFree(ctx->region_plane);
+        ctx->region_text = nullptr; ctx->region_plane = nullptr; ctx->region_cap = 0;
+        CK(cudaMalloc(&ctx->region_text, (size_t)n_regions * 4));
+        CK(cudaMalloc(&ctx->region_plane, (size_t)n_regions * 16));
+        ctx->region_cap = n_regions;
+    }
     CK(cudaMemcpyAsync(ctx->region_text, text, (size_t)n_regions * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->region_plane, norm4, (size_t)n_regions * 16, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
