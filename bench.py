@@ -261,9 +261,12 @@ def run_ours(args):
         step_e2e(lane, SEED)
     barrier(world)
     t0 = time.perf_counter()
+    def lane_worker(j):                     # one host thread per lane: a context is never used by two threads
+        for k in range(j, args.steps, 2):
+            step_e2e(lanes[j], SEED + 100 * k)
+
     with cf.ThreadPoolExecutor(2) as pool:
-        futs = [pool.submit(step_e2e, lanes[k % 2], SEED + 100 * k) for k in range(args.steps)]
-        for f in futs:
+        for f in [pool.submit(lane_worker, j) for j in range(2)]:
             f.result()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)

@@ -288,6 +288,8 @@ def test_dataset_readers_roundtrip(tmp_path, pkg, tiny):
     # reference view = image 2: the list is [2, 0, 1, 3]; pair.txt lists neighbours 0, 1, 3 -> list positions 1, 2, 3
     assert cli.read_pair_subset(str(tmp_path / "pair.txt"), 2) == [1, 2, 3]
     assert cli.read_pair_subset(str(tmp_path / "pair.txt"), 0) == [1, 2, 3]
+    assert cli.read_pair_neighbours(str(tmp_path / "pair.txt"), 2) == [0, 1, 3]
+    assert cli.parse_args(["-all_views", "-mslp_folder", "x/"])["all_views"] is True
     import cv2
     im = cv2.imread(str(tmp_path / "images" / names[1]), cv2.IMREAD_GRAYSCALE)
     assert np.array_equal(im.astype(np.float32), tiny["images"][1])

@@ -500,3 +500,32 @@ def test_cli_end_to_end_on_synthetic_dataset(env, tmp_path):
     assert depth.shape == (scene["H"], scene["W"]) and normal.shape == (scene["H"], scene["W"], 3)
     assert pc.frac_bit_exact(depth, out[..., 3]) == 1.0
     assert pc.frac_bit_exact(normal, np.ascontiguousarray(out[..., :3])) == 1.0
+
+
+def test_cli_all_views_resident_pool(env, tmp_path):
+    """`-all_views`: every image is the reference view once, images resident on the GPU, two pipelined contexts.
+    View 0 must equal the one-view command line bit for bit; every view must produce its three files."""
+    import subprocess
+    import sys
+    pkg, rb = env
+    from tsar_mvs_b200 import dmb
+    root = str(tmp_path / "ds") + "/"
+    common = ["-mslp_folder", root, "-krt_file", "x", "-no_display", "--cam_scale=1", "--iterations=2", "--blocksize=11",
+              "--cost_comb=best_n", "--n_best=1", f"--seed={SEED}"]
+    r = subprocess.run([sys.executable, os.path.join(pc.ROOT, "tsar_cli.py"), "--synthetic=tiny"] + common,
+                       capture_output=True, text=True, cwd=pc.ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    one = dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_disp.dmb"))
+    one_n = dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_normals.dmb"))
+    os.remove(os.path.join(root, "APD", "00000000", "TSAR_disp.dmb"))
+    r = subprocess.run([sys.executable, os.path.join(pc.ROOT, "tsar_cli.py"), "-all_views", "-images_folder", root + "images/"] + common,
+                       capture_output=True, text=True, cwd=pc.ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    n = pkg.scene.CONFIGS["tiny"]["n_images"]
+    assert f"{n} of {n} reference views" in r.stdout
+    for v in range(n):
+        d = dmb.read_dmb(os.path.join(root, "APD", f"{v:08d}", "TSAR_disp.dmb"))
+        assert d.shape == one.shape and np.isfinite(d).all() and (d > 0).mean() > 0.5
+        assert os.path.exists(os.path.join(root, "APD", f"{v:08d}", "TSAR_confidence.dmb"))
+    assert pc.frac_bit_exact(dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_disp.dmb")), one) == 1.0
+    assert pc.frac_bit_exact(dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_normals.dmb")), one_n) == 1.0

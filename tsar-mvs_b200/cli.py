@@ -20,6 +20,12 @@ Textureless-region completion needs the weak-texture detector of main.cpp:365-59
 f3, not built): pass a precomputed label map with `-regions_file labels.npy` (+ `-regions_text text.npy`) to enable
 plane fitting (tsar_fit_region_planes) and depth completion.
 Extra: `--synthetic=<C1|C2|small|tiny>` first writes a synthetic dataset in the reference's folder layout.
+
+`-all_views` replaces the per-view process loop of the run scripts (scripts/pipes.sh:30-49): every image of the
+dataset becomes the reference view once.  All images are decoded and uploaded ONCE and stay resident in HBM; each
+reference view binds itself + its pair.txt neighbours from that pool (device-to-device), two contexts on two streams
+pipeline view r+1 behind view r, results are written by the worker threads.  Under torchrun the views are sharded
+round-robin over the ranks (shard.py), one GPU per rank, no collective.
 """
 import os
 import sys
@@ -34,14 +40,14 @@ NUMERIC = {"blocksize", "iterations", "n_best", "cost_gamma", "depth_min", "dept
            "self_similarity_n", "good_factor", "num_img_processed", "seed", "synthetic", "device"}
 PATHS = {"images_folder", "mslp_folder", "krt_file", "output_folder", "p_folder", "camera_folder", "calib_file", "pmvs_folder",
          "bounding_folder", "regions_file", "regions_text", "regions_size"}
-BOOLS = {"color_processing", "view_selection", "import_apd", "no_display"}
+BOOLS = {"color_processing", "view_selection", "import_apd", "no_display", "all_views"}
 
 
 def parse_args(argv):
     """getParametersFromCommandLine (main.cpp:708-1009), tolerant in the same places."""
     opt = dict(images=[], blocksize=19, iterations=8, n_best=2, cost_comb=1, cam_scale=1.0, depth_min=-1.0, depth_max=-1.0,
                seed=20240601, device=0, images_folder="", mslp_folder="", output_folder="", synthetic=None,
-               color_processing=False, import_apd=False, regions_file=None, regions_text=None, regions_size=None)
+               color_processing=False, import_apd=False, all_views=False, regions_file=None, regions_text=None, regions_size=None)
     i = 0
     while i < len(argv):
         a = argv[i]
@@ -152,6 +158,8 @@ def run(argv):
         _, names = write_synthetic_dataset(opt["synthetic"], mslp)
         opt["images"] = opt["images"] or names
         opt["images_folder"] = os.path.join(mslp, "images/")
+    if opt["all_views"]:
+        return run_all_views(opt, mslp)
     if not opt["images"]:
         print(__doc__)
         return 2
@@ -216,6 +224,87 @@ def run(argv):
     dmb.write_dmb(os.path.join(out_dir, "TSAR_confidence.dmb"), confid)   # computed but never written by the reference
     print(f"[tsar_cli] {stem}: {W}x{H}, {len(subset)} source views -> {out_dir}/TSAR_disp.dmb, TSAR_normals.dmb")
     eng.close()
+    return 0
+
+
+def read_pair_neighbours(path, camera_id):
+    """Camera ids of the source views of `camera_id` in pair.txt order (main.cpp:1351-1376)."""
+    lines = open(path).read().split("\n")
+    line = lines[2 * camera_id + 2].split()
+    return [int(line[1 + 2 * j]) for j in range(int(line[0]))]
+
+
+def run_all_views(opt, mslp):
+    """Persistent multi-view driver (SURVEY section 8 rows e/f4): see the module docstring."""
+    import concurrent.futures as cf
+    import time
+
+    import torch
+
+    from . import _lib as L
+    from .shard import views_for_rank
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    ndev = torch.cuda.device_count()
+    if ndev == 0:
+        raise RuntimeError("tsar_cli -all_views needs a CUDA device (no CPU path)")
+    dev = int(os.environ.get("LOCAL_RANK", opt["device"])) % ndev
+    folder = opt["images_folder"] or os.path.join(mslp, "images/")
+    names = opt["images"] or sorted(n for n in os.listdir(folder) if n.lower().endswith((".jpg", ".jpeg", ".png", ".npy")))
+    ids = [int(n[4:8]) for n in names]                          # camera id of each image (main.cpp:1347-1349)
+    by_id = {c: k for k, c in enumerate(ids)}
+    krt = [read_cam_txt(os.path.join(mslp, "cams", f"{n[:8]}_cam.txt")) for n in names]
+    t0 = time.perf_counter()
+    pool = [torch.from_numpy(_imread_gray(os.path.join(folder, n))).to(f"cuda:{dev}") for n in names]   # resident, once
+    H, W = pool[0].shape
+    mine = views_for_rank(len(names), rank, world)
+    lanes = []
+    for _ in range(min(2, max(1, len(mine)))):
+        st = torch.cuda.Stream(device=dev)
+        lanes.append(dict(eng=DepthmapEngine(dev, stream=st.cuda_stream), stream=st))
+    done = []
+
+    def process(k, lane):
+        eng = lane["eng"]
+        r = mine[k]
+        nb = [by_id[c] for c in read_pair_neighbours(os.path.join(mslp, "pair.txt"), ids[r]) if c in by_id]
+        sel = [r] + nb
+        Ks = []
+        for i in sel:
+            K = krt[i][0].copy()
+            K[:2] /= opt["cam_scale"]
+            Ks.append(K)
+        dmin = opt["depth_min"] if opt["depth_min"] > 0 else krt[r][3]
+        dmax = opt["depth_max"] if opt["depth_max"] > 0 else krt[r][4]
+        cams = scene.cameras_from_krt(Ks, [krt[i][1] for i in sel], [krt[i][2] for i in sel], dmin, dmax)
+        f = float(np.float32(cams[0]["f"]))
+        params = make_params(box=opt["blocksize"], iterations=opt["iterations"], n_best=opt["n_best"], cost_comb=opt["cost_comb"],
+                             min_disparity=float(np.float32(f / np.float32(dmax))), max_disparity=float(np.float32(f / np.float32(dmin))))
+        from .engine import cameras_to_struct
+        eng.set_views_device([pool[i].data_ptr() for i in sel], W, H, cameras_to_struct(cams), list(range(1, len(sel))), cam_f=f)
+        eng.set_params(params)
+        eng.init_planes(int(opt["seed"]) + r)
+        eng.iterate(opt["iterations"], int(opt["seed"]) + r)
+        eng.lrdiff(); eng.getview(); eng.compute_disp()
+        out, confid = eng.download(L.F_NORM4), eng.download(L.F_CONFID)
+        out_dir = os.path.join(mslp, "APD", names[r][:8])
+        dmb.write_outputs(out_dir, out)
+        dmb.write_dmb(os.path.join(out_dir, "TSAR_confidence.dmb"), confid)
+        done.append(r)
+        return r
+
+    def lane_worker(j):                                         # one host thread per lane: a context is never shared
+        for k in range(j, len(mine), len(lanes)):
+            process(k, lanes[j])
+
+    with cf.ThreadPoolExecutor(len(lanes)) as ex:
+        for fu in [ex.submit(lane_worker, j) for j in range(len(lanes))]:
+            fu.result()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    for lane in lanes:
+        lane["eng"].close()
+    print(f"[tsar_cli] rank {rank}/{world}: {len(done)} of {len(names)} reference views ({W}x{H}) in {dt:.2f} s "
+          f"({len(done) / dt:.2f} depthmaps/s incl. decoding and .dmb writing) -> {os.path.join(mslp, 'APD')}")
     return 0
 
 
