@@ -159,6 +159,27 @@ int tsar_fit_region_planes(tsar_ctx *ctx, int n_regions, const float *region_tex
                            const uint32_t *rnd, float *region_norm4);
 int tsar_ransac_rand_per_region(void);
 
+/* ---- weak-texture region detector: texture() in main.cpp:365-596 --------------------
+ * Host functions (sequential raster scans whose results depend on the scan order; the reference runs them on the
+ * quarter-resolution grey image, <= 0.4 Mpx at C2).  The OpenCV stages in between -- pyrDown x2 before, HoughLinesP +
+ * line() per weak label between the two labellings -- stay with the caller, who has OpenCV (the reference's main.cpp,
+ * or tsar-mvs_b200/texture.py).  All buffers are host memory, row-major w x h. */
+/* roberts() main.cpp:214-240 + cv::threshold(.., thr, 255, THRESH_BINARY) main.cpp:383; thr = Robthr = 4 */
+int tsar_weak_edges(const unsigned char *gray, int w, int h, int thr, unsigned char *edges);
+/* Connect() main.cpp:242-362: labels (0 = edge), per-label pixel counts (cap entries available), label count */
+int tsar_weak_connect(const unsigned char *edges, int w, int h, int *labels, int *label_count, int cap, int *n_labels);
+/* boundary image of one label, the input of HoughLinesP (main.cpp:392-421) */
+int tsar_weak_boundary(const int *labels, int w, int h, int label, unsigned char *gray);
+/* border closing before the second labelling (main.cpp:441-454), in place */
+int tsar_weak_close_border(unsigned char *edges, int w, int h);
+/* region statistics + weak decision (main.cpp:478-536, 570-593): cannylines->text / cenxi / cenyi / size;
+ * min_pixels = weaktextnum = 5000, size_ratio = (int)sizerat = 2 */
+int tsar_weak_regions(const int *labels, int w, int h, const int *label_count, int n_labels, int min_pixels,
+                      int size_ratio, float *text, int *cenxi, int *cenyi, float *size);
+/* lines->canny[] from the quarter-resolution label map (main.cpp:558-568), expanded on the device: 1/16 of the
+ * host-to-device bytes of uploading the full-resolution float map. */
+int tsar_set_labels_quarter(tsar_ctx *ctx, const int *labels, int wq, int hq);
+
 /* ---- state transfer --------------------------------------------------------------------------- */
 int tsar_upload(tsar_ctx *ctx, int field, const void *host_src, size_t bytes);
 int tsar_download(tsar_ctx *ctx, int field, void *host_dst, size_t bytes);

@@ -293,3 +293,81 @@ def test_dataset_readers_roundtrip(tmp_path, pkg, tiny):
     import cv2
     im = cv2.imread(str(tmp_path / "images" / names[1]), cv2.IMREAD_GRAYSCALE)
     assert np.array_equal(im.astype(np.float32), tiny["images"][1])
+
+
+# ---- weak-texture region detector: host functions vs the plain-Python restatement ----------
+def _detector_inputs():
+    rng = np.random.RandomState(5)
+    yy, xx = np.mgrid[0:38, 0:53]
+    smooth = (120 + 60 * np.sin(xx / 7.0) * np.cos(yy / 5.0)).astype(np.uint8)
+    noisy = smooth.copy()
+    noisy[:, 20:40] = rng.randint(0, 256, (38, 20))                       # a textured band between two flat areas
+    hard = np.where((xx + yy) % 2 == 0, 0, 255).astype(np.uint8)          # magnitudes >= 256: the low-byte quirk
+    hard[10:20, 10:30] = 200
+    steps = (np.arange(53)[None, :] * np.ones((38, 1))).astype(np.uint8)  # magnitude sqrt(2) everywhere
+    steps[5:30, 8:45] = (181 * ((xx[5:30, 8:45] + yy[5:30, 8:45]) % 2)).astype(np.uint8)  # t1+t2 = 2*181^2 = 65522 / 0
+    stripes = (255 * (xx % 2)).astype(np.uint8)                           # magnitude 360 -> stored as 104
+    stripes[20:22, 30:32] = [[255, 0], [30, 0]]                           # 255^2 + 30^2 = 65925 -> 256 -> stored as 0
+    return [smooth, noisy, hard, steps, stripes]
+
+
+def test_weak_texture_stages_match_restatement(pkg):
+    """tsar_weak_* (libtsar_b200.so host functions) against oracle/weak_texture_ref.py: Roberts + threshold, the
+    two-pass labelling with the reference's own equivalence table (order dependent), boundary images, border closing,
+    region statistics and the weak decision, the label expansion to full resolution."""
+    from oracle import weak_texture_ref as wr
+    from tsar_mvs_b200 import texture as tx
+    rng = np.random.RandomState(11)
+    for gray in _detector_inputs():
+        for thr in (4, 40):
+            e = tx.edges(gray, thr)
+            assert np.array_equal(e, wr.roberts_threshold(gray, thr))
+    assert tx.edges(_detector_inputs()[4], 4)[20, 30] == 0 and tx.edges(_detector_inputs()[4], 4)[5, 5] == 255
+    # labelling: random edge maps of several densities provoke every branch, including lost equivalences
+    split_seen = False
+    for density in (0.15, 0.3, 0.45, 0.6):
+        for trial in range(3):
+            e = np.where(rng.rand(31, 44) < density, 255, 0).astype(np.uint8)
+            lab, cnt = tx.connect(e)
+            lab_r, cnt_r = wr.connect(e)
+            assert np.array_equal(lab, lab_r) and np.array_equal(cnt, cnt_r)
+            assert cnt.sum() == e.size and cnt[0] == (e == 255).sum()
+            from scipy import ndimage
+            true_n = ndimage.label(e == 0)[1]
+            assert len(cnt) - 1 >= true_n            # never fewer labels than true 4-connected components ...
+            split_seen |= (len(cnt) - 1 > true_n)    # ... and sometimes more: the table loses equivalences
+            k = int(np.argmax(cnt[1:])) + 1
+            assert np.array_equal(tx.boundary(lab, k), wr.boundary(lab_r, k))
+            assert np.array_equal(tx.close_border(e), wr.close_border(e))
+            for weaktextnum in (5, 60):
+                got = tx.regions(lab, cnt, weaktextnum, 2)
+                want = wr.regions(lab_r, cnt_r, weaktextnum, 2)
+                for g, w_ in zip(got, want):
+                    assert np.array_equal(g, w_)
+            assert np.array_equal(tx.expand_labels(lab, 4 * 44 + 3, 4 * 31 + 2), wr.expand(lab_r, 4 * 44 + 3, 4 * 31 + 2))
+    assert split_seen, "test inputs never exercised the order-dependent equivalence table"
+
+
+def test_weak_texture_detector_finds_the_textureless_facet(pkg):
+    """texture() end to end (cv2 for pyrDown / HoughLinesP / line, as the reference uses OpenCV): on the synthetic
+    scene the untextured facet must come out as a weakly textured region (text = -1), the label map must cover the
+    image, and textured ground must not be flagged."""
+    pytest.importorskip("cv2")
+    from tsar_mvs_b200 import scene, texture as tx
+    cfg = dict(W=1280, H=960, n_images=2, V=1, fx=720.0, radius=4.0, arc_deg=10.0)
+    cams = scene.make_cameras(cfg["W"], cfg["H"], cfg["n_images"], cfg["fx"], cfg["radius"], cfg["arc_deg"])
+    sc = scene.Scene(cfg["W"], cfg["H"], cfg["fx"], cfg["radius"])
+    img, _, labels = sc.render(cams[0], cfg["W"], cfg["H"])
+    det = tx.detect(img.astype(np.uint8), min_pixels=2000)
+    lab = det["labels_q"]
+    assert lab.shape == (240, 320) and det["label_count"].sum() == lab.size
+    facet_q = labels[::4, ::4][:240, :320] == 4                 # generator label of the untextured facet
+    weak = det["text"][lab] == -1.0
+    assert weak[facet_q].mean() > 0.7, weak[facet_q].mean()     # most of the facet is inside a weak region
+    assert weak[~facet_q].mean() < 0.2, weak[~facet_q].mean()   # and weak regions are mostly the facet
+    k = int(np.bincount(lab[facet_q]).argmax())
+    assert det["text"][k] == -1.0 and det["size"][k] > 50
+    cx, cy = det["cenxi"][k], det["cenyi"][k]
+    assert labels[min(cy, cfg["H"] - 1), min(cx, cfg["W"] - 1)] == 4   # centroid (full-resolution pixels) lies on the facet
+    full = tx.expand_labels(lab, cfg["W"], cfg["H"])
+    assert full.shape == (cfg["H"], cfg["W"]) and full[5, 7] == lab[1, 1]

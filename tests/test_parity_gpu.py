@@ -529,3 +529,57 @@ def test_cli_all_views_resident_pool(env, tmp_path):
         assert os.path.exists(os.path.join(root, "APD", f"{v:08d}", "TSAR_confidence.dmb"))
     assert pc.frac_bit_exact(dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_disp.dmb")), one) == 1.0
     assert pc.frac_bit_exact(dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_normals.dmb")), one_n) == 1.0
+
+
+def test_labels_quarter_expansion_on_device(env):
+    """lines->canny from the quarter-resolution region labels (main.cpp:558-568), expanded by a kernel: equals the
+    plain-Python restatement, including the stepped-back last column/row of sizes that are not multiples of 4."""
+    pkg, rb = env
+    L = pkg._lib
+    from oracle import weak_texture_ref as wr
+    cfg = dict(W=67, H=33, n_images=2, V=1, fx=150.0, radius=1.0, arc_deg=14.0)
+    scene = pkg.scene.make_scene(cfg)
+    params, mine, _ = pc.make_engines(pkg, scene, variants=())
+    lab = np.random.RandomState(2).randint(0, 9, size=(33 // 2 // 2, 67 // 2 // 2)).astype(np.int32)
+    mine.set_labels_quarter(lab)
+    got = mine.download(L.F_CANNY)
+    assert np.array_equal(got, wr.expand(lab, 67, 33))
+    assert np.array_equal(got, pkg.texture.expand_labels(lab, 67, 33))
+    with pytest.raises(Exception):
+        mine.set_labels_quarter(lab[:, :5])
+    mine.close()
+
+
+def test_cli_full_tsar_flow_with_detector(env, tmp_path):
+    """The whole TSAR flow from files: weak-texture detector (texture.py) -> PatchMatch -> confidence -> per-region
+    RANSAC plane on the device -> depth completion -> .dmb.  The untextured facet must end up closer to the ground
+    truth than without completion (`-no_weak_texture`)."""
+    import subprocess
+    import sys
+    pkg, rb = env
+    from tsar_mvs_b200 import dmb
+    root = str(tmp_path / "ds") + "/"
+    common = ["-mslp_folder", root, "-krt_file", "x", "-no_display", "--cam_scale=1", "--iterations=4", "--blocksize=11",
+              "--cost_comb=best_n", "--n_best=1", f"--seed={SEED}"]
+    r = subprocess.run([sys.executable, os.path.join(pc.ROOT, "tsar_cli.py"), "--synthetic=mid"] + common,
+                       capture_output=True, text=True, cwd=pc.ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "weakly textured" in r.stdout
+    with_fill = dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_disp.dmb"))
+    names = sorted(os.listdir(root + "images"))
+    r2 = subprocess.run([sys.executable, os.path.join(pc.ROOT, "tsar_cli.py")] + names + ["-images_folder", root + "images/", "-no_weak_texture"] + common,
+                        capture_output=True, text=True, cwd=pc.ROOT)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    without = dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_disp.dmb"))
+    cfg = pkg.scene.CONFIGS["mid"]
+    cams = pkg.scene.make_cameras(cfg["W"], cfg["H"], cfg["n_images"], cfg["fx"], cfg["radius"], cfg["arc_deg"])
+    _, gt, labels = pkg.scene.Scene(cfg["W"], cfg["H"], cfg["fx"], cfg["radius"]).render(cams[0], cfg["W"], cfg["H"])
+    flat = labels == 4
+    err_fill = np.abs(with_fill - gt)[flat] / gt[flat]
+    err_raw = np.abs(without - gt)[flat] / gt[flat]
+    print(f"\n[facet] median rel. depth error: completed {np.median(err_fill):.4f}, PatchMatch only {np.median(err_raw):.4f}; "
+          f"within 2 %: {np.mean(err_fill < 0.02):.3f} vs {np.mean(err_raw < 0.02):.3f}\n{r.stdout[-400:]}")
+    assert np.mean(err_fill < 0.02) > 0.9 > np.mean(err_raw < 0.02)
+    assert np.median(err_fill) < 0.01
+    ground = (labels == 0) & (without > 0)
+    assert np.mean(with_fill[ground] == without[ground]) > 0.95   # textured regions are left as PatchMatch found them

@@ -52,6 +52,7 @@ EXPORTS = [
     "tsar_getview", "tsar_get_disp", "tsar_update_scale_2", "tsar_update_scale", "tsar_compute_disp", "tsar_wmf",
     "tsar_wmf_final", "tsar_set_regions", "tsar_fit_region_planes", "tsar_ransac_rand_per_region", "tsar_upload", "tsar_download", "tsar_device_ptr", "tsar_depthmap",
     "tsar_depthmap_host", "tsar_slic", "tsar_launch_count", "tsar_eval_count", "tsar_version", "tsar_dbg_tex_sample", "tsar_dbg_peaks", "tsar_dbg_eval_rounding", "tsar_dbg_tex_formats", "tsar_profile", "tsar_profile_read",
+    "tsar_weak_edges", "tsar_weak_connect", "tsar_weak_boundary", "tsar_weak_close_border", "tsar_weak_regions", "tsar_set_labels_quarter",
 ]
 
 
@@ -108,6 +109,12 @@ def load():
         "tsar_dbg_tex_formats": (i, [vp, i, i, vp, vp, vp]),
         "tsar_profile": (i, [vp, i]),
         "tsar_profile_read": (i, [vp, fp, ip]),
+        "tsar_weak_edges": (i, [vp, i, i, i, vp]),
+        "tsar_weak_connect": (i, [vp, i, i, vp, vp, i, ip]),
+        "tsar_weak_boundary": (i, [vp, i, i, i, vp]),
+        "tsar_weak_close_border": (i, [vp, i, i]),
+        "tsar_weak_regions": (i, [vp, i, i, vp, i, i, i, vp, vp, vp, vp]),
+        "tsar_set_labels_quarter": (i, [vp, vp, i, i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

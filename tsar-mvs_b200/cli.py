@@ -16,9 +16,10 @@ Flows:
   * default (north-star): random initialisation + red/black PatchMatch + L/R check + confidence + output layout;
   * `-import_apd`: the shipped flow -- planes imported from `<mslp>/APD/<stem>/depths_geom.dmb` + `normals.dmb`
     (main.cpp:1459-1490) then gipuma_get_disp / getview / output.
-Textureless-region completion needs the weak-texture detector of main.cpp:365-596 (OpenCV HoughLinesP; SURVEY row
-f3, not built): pass a precomputed label map with `-regions_file labels.npy` (+ `-regions_text text.npy`) to enable
-plane fitting (tsar_fit_region_planes) and depth completion.
+Textureless-region completion: the weak-texture detector of main.cpp:365-596 (texture.py; cv2 for pyrDown /
+HoughLinesP / line as the reference uses OpenCV) labels the reference view; regions it flags get a plane from
+tsar_fit_region_planes and are completed by update_scale(_2).  `-no_weak_texture` skips it; `-regions_file labels.npy`
+(+ `-regions_text text.npy`) supplies a precomputed label map instead.
 Extra: `--synthetic=<C1|C2|small|tiny>` first writes a synthetic dataset in the reference's folder layout.
 
 `-all_views` replaces the per-view process loop of the run scripts (scripts/pipes.sh:30-49): every image of the
@@ -40,14 +41,14 @@ NUMERIC = {"blocksize", "iterations", "n_best", "cost_gamma", "depth_min", "dept
            "self_similarity_n", "good_factor", "num_img_processed", "seed", "synthetic", "device"}
 PATHS = {"images_folder", "mslp_folder", "krt_file", "output_folder", "p_folder", "camera_folder", "calib_file", "pmvs_folder",
          "bounding_folder", "regions_file", "regions_text", "regions_size"}
-BOOLS = {"color_processing", "view_selection", "import_apd", "no_display", "all_views"}
+BOOLS = {"color_processing", "view_selection", "import_apd", "no_display", "all_views", "no_weak_texture"}
 
 
 def parse_args(argv):
     """getParametersFromCommandLine (main.cpp:708-1009), tolerant in the same places."""
     opt = dict(images=[], blocksize=19, iterations=8, n_best=2, cost_comb=1, cam_scale=1.0, depth_min=-1.0, depth_max=-1.0,
                seed=20240601, device=0, images_folder="", mslp_folder="", output_folder="", synthetic=None,
-               color_processing=False, import_apd=False, all_views=False, regions_file=None, regions_text=None, regions_size=None)
+               color_processing=False, import_apd=False, all_views=False, no_weak_texture=False, regions_file=None, regions_text=None, regions_size=None)
     i = 0
     while i < len(argv):
         a = argv[i]
@@ -205,12 +206,22 @@ def run(argv):
         eng.lrdiff()
     eng.getview()
     confid = eng.download(L.F_CONFID)
+    text = size = None
     if opt["regions_file"]:
         labels = np.load(opt["regions_file"]).astype(np.float32)
         text = np.load(opt["regions_text"]).astype(np.float32)
         size = np.load(opt["regions_size"]).astype(np.float32) if opt["regions_size"] else \
             np.array([(labels == r).sum() / 16.0 for r in range(len(text))], np.float32)
         eng.upload(L.F_CANNY, labels)
+    elif not opt["no_weak_texture"]:            # texture() runs first in the reference's main (main.cpp:1896)
+        from . import texture
+        det = texture.detect(images[0].astype(np.uint8))
+        n_weak = int((det["text"] == -1).sum())
+        print(f"[tsar_cli] weak-texture detector: {len(det['text']) - 1} regions, {n_weak} weakly textured")
+        if n_weak:
+            text, size = det["text"], det["size"]
+            eng.set_labels_quarter(det["labels_q"])
+    if text is not None:
         eng.upload(L.F_SCALE, (confid > 0.8).astype(np.float32))       # reliable pixels (stands in for APD's weak.png)
         rng = np.random.RandomState(int(opt["seed"]) & 0x7fffffff)
         rnd = rng.randint(0, 2 ** 31 - 1, size=(len(text), eng.lib.tsar_ransac_rand_per_region())).astype(np.uint32)

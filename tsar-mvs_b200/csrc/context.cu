@@ -722,6 +722,23 @@ int tsar_set_regions(tsar_ctx *ctx, int n_regions, const float *text, const floa
     return TSAR_OK;
 }
 
+int tsar_set_labels_quarter(tsar_ctx *ctx, const int *labels, int wq, int hq) {
+    if (!ctx || !labels) return TSAR_ERR_ARG;
+    if (!ctx->have_views) FAIL(TSAR_ERR_STATE, "tsar_set_views has not been called");
+    if (wq < 1 || hq < 1 || 4 * (wq + 1) < ctx->W || 4 * (hq + 1) < ctx->H || 4 * wq > ctx->W + 3 || 4 * hq > ctx->H + 3)
+        FAIL(TSAR_ERR_ARG, "label map is not the quarter-resolution grid of the views");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_scratch(ctx, (size_t)wq * hq * 4);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->scratch, labels, (size_t)wq * hq * 4, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 b(32, 8), g((ctx->W + 31) / 32, (ctx->H + 7) / 8);
+    labels_quarter_kernel<<<g, b, 0, ctx->stream>>>((const int *)ctx->scratch, wq, hq, ctx->W, ctx->H, ctx->canny);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaStreamSynchronize(ctx->stream));  // the caller's buffer may go away
+    return TSAR_OK;
+}
+
 int tsar_fit_region_planes(tsar_ctx *ctx, int n_regions, const float *region_text, const float *region_size,
                            const uint32_t *rnd, float *region_norm4) {
     int rc = need_ready(ctx);

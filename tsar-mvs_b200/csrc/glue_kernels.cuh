@@ -232,4 +232,15 @@ __global__ void update_scale_2_kernel(const __grid_constant__ GlueConst g, float
     }
 }
 
+// canny[] from the quarter-resolution region labels (main.cpp:558-568): label of (y/4, x/4), the index stepped
+// back once where the twice-halved size is smaller than ceil(size/4).  Labels stay float at the boundary (Q13).
+__global__ void labels_quarter_kernel(const int *__restrict__ lab, int wq, int hq, int W, int H, float *__restrict__ canny) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    int sx = x / 4, sy = y / 4;
+    if (sx >= wq) sx--;
+    if (sy >= hq) sy--;
+    canny[(size_t)y * W + x] = (float)lab[(size_t)sy * wq + sx];
+}
+
 }  // namespace tsar

@@ -101,6 +101,12 @@ class DepthmapEngine:
         norm4 = np.ascontiguousarray(norm4, np.float32).reshape(-1, 4)
         self._ck(self.lib.tsar_set_regions(self.h, len(text), text.ctypes.data, norm4.ctypes.data), "tsar_set_regions")
 
+    def set_labels_quarter(self, labels_q):
+        """lines->canny from the quarter-resolution region labels of texture.detect (main.cpp:558-568), expanded on
+        the device."""
+        lab = np.ascontiguousarray(labels_q, np.int32)
+        self._ck(self.lib.tsar_set_labels_quarter(self.h, lab.ctypes.data, lab.shape[1], lab.shape[0]), "tsar_set_labels_quarter")
+
     def fit_region_planes(self, region_text, region_size, rnd, region_norm4):
         """Per-region RANSAC plane fit (main.cpp:1520-1730) for regions with text == -1; rnd: [n_regions][46000]
         uint32 (the values rand() would return).  Returns the updated [n_regions][4] planes."""

@@ -16,6 +16,7 @@ CONFIGS = {
     "C2": dict(W=3100, H=2050, n_images=11, V=10, fx=1750.0, radius=4.0, arc_deg=30.0),    # ETH3D pipes-shaped
     "C4": dict(W=1920, H=1080, n_images=11, V=10, fx=1160.0, radius=5.0, arc_deg=30.0),    # Tanks&Temples-shaped
     "C5": dict(W=6048, H=4032, n_images=21, V=20, fx=3410.0, radius=6.0, arc_deg=40.0),    # full-resolution stress
+    "mid": dict(W=1280, H=960, n_images=5, V=4, fx=720.0, radius=4.0, arc_deg=16.0),       # detector + completion tests
     "tiny": dict(W=96, H=64, n_images=4, V=3, fx=180.0, radius=1.0, arc_deg=16.0),         # unit tests / golden
     "small": dict(W=320, H=240, n_images=6, V=5, fx=800.0, radius=1.0, arc_deg=20.0),      # GPU parity tests
 }
