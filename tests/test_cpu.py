@@ -371,3 +371,31 @@ def test_weak_texture_detector_finds_the_textureless_facet(pkg):
     assert labels[min(cy, cfg["H"] - 1), min(cx, cfg["W"] - 1)] == 4   # centroid (full-resolution pixels) lies on the facet
     full = tx.expand_labels(lab, cfg["W"], cfg["H"])
     assert full.shape == (cfg["H"], cfg["W"]) and full[5, 7] == lab[1, 1]
+
+
+def test_model_ply_writer(tmp_path, pkg, tiny):
+    """TSAR_model.ply (displayUtils.h:77-158): header, column-major vertex order, world points that reproject onto
+    their pixel at their depth with the untransformed camera (cameraGeometryUtils.h:53-65)."""
+    from tsar_mvs_b200 import dmb
+    cam = tiny["cams"][0]
+    H, W = tiny["H"], tiny["W"]
+    depth = tiny["gt_depth"].astype(np.float32)
+    depth[3, 5] = np.inf                                            # a non-finite point is written as the origin
+    normals = np.zeros((H, W, 3), np.float32); normals[..., 2] = -1
+    R, C = cam["_R_world"], cam["_C_world"]
+    t = -R @ C
+    path = str(tmp_path / "TSAR_model.ply")
+    dmb.write_model_ply(path, depth, normals, tiny["images"][0], cam["K"], R, t)
+    head = open(path, "rb").read(400).decode("latin1")
+    assert head.startswith("ply\nformat binary_little_endian 1.0\n") and f"element vertex {H * W}\n" in head
+    pts, nrm, col = dmb.read_model_ply(path)
+    assert pts.shape == (H * W, 3) and os.path.getsize(path) == head.index("end_header\n") + 11 + 27 * H * W
+    P = cam["K"] @ np.concatenate([R, t[:, None]], 1)
+    for (x, y) in ((0, 0), (10, 7), (W - 1, H - 1), (50, 33)):
+        X = pts[x * H + y].astype(np.float64)                       # x outer, y inner
+        p = P @ np.append(X, 1.0)
+        assert abs(p[2] - depth[y, x]) < 1e-3 * depth[y, x]
+        assert abs(p[0] / p[2] - x) < 1e-2 and abs(p[1] / p[2] - y) < 1e-2
+        assert col[x * H + y].tolist() == [int(tiny["images"][0][y, x])] * 3
+    assert np.array_equal(pts[5 * H + 3], np.zeros(3, np.float32))
+    assert np.array_equal(nrm[7], normals[7, 0])

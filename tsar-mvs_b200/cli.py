@@ -20,6 +20,7 @@ Textureless-region completion: the weak-texture detector of main.cpp:365-596 (te
 HoughLinesP / line as the reference uses OpenCV) labels the reference view; regions it flags get a plane from
 tsar_fit_region_planes and are completed by update_scale(_2).  `-no_weak_texture` skips it; `-regions_file labels.npy`
 (+ `-regions_text text.npy`) supplies a precomputed label map instead.
+`-write_ply` also writes `TSAR_model.ply` (displayUtils.h:77-158).
 Extra: `--synthetic=<C1|C2|small|tiny>` first writes a synthetic dataset in the reference's folder layout.
 
 `-all_views` replaces the per-view process loop of the run scripts (scripts/pipes.sh:30-49): every image of the
@@ -41,14 +42,14 @@ NUMERIC = {"blocksize", "iterations", "n_best", "cost_gamma", "depth_min", "dept
            "self_similarity_n", "good_factor", "num_img_processed", "seed", "synthetic", "device"}
 PATHS = {"images_folder", "mslp_folder", "krt_file", "output_folder", "p_folder", "camera_folder", "calib_file", "pmvs_folder",
          "bounding_folder", "regions_file", "regions_text", "regions_size"}
-BOOLS = {"color_processing", "view_selection", "import_apd", "no_display", "all_views", "no_weak_texture"}
+BOOLS = {"color_processing", "view_selection", "import_apd", "no_display", "all_views", "no_weak_texture", "write_ply"}
 
 
 def parse_args(argv):
     """getParametersFromCommandLine (main.cpp:708-1009), tolerant in the same places."""
     opt = dict(images=[], blocksize=19, iterations=8, n_best=2, cost_comb=1, cam_scale=1.0, depth_min=-1.0, depth_max=-1.0,
                seed=20240601, device=0, images_folder="", mslp_folder="", output_folder="", synthetic=None,
-               color_processing=False, import_apd=False, all_views=False, no_weak_texture=False, regions_file=None, regions_text=None, regions_size=None)
+               color_processing=False, import_apd=False, all_views=False, no_weak_texture=False, write_ply=False, regions_file=None, regions_text=None, regions_size=None)
     i = 0
     while i < len(argv):
         a = argv[i]
@@ -233,6 +234,8 @@ def run(argv):
     out = eng.download(L.F_NORM4)
     dmb.write_outputs(out_dir, out)
     dmb.write_dmb(os.path.join(out_dir, "TSAR_confidence.dmb"), confid)   # computed but never written by the reference
+    if opt["write_ply"]:                        # main.cpp:1836-1843 (always on there; 27 B per pixel, so opt-in here)
+        dmb.write_model_ply(os.path.join(out_dir, "TSAR_model.ply"), out[..., 3], out[..., :3], images[0], Ks[0], Rs[0], ts[0])
     print(f"[tsar_cli] {stem}: {W}x{H}, {len(subset)} source views -> {out_dir}/TSAR_disp.dmb, TSAR_normals.dmb")
     eng.close()
     return 0
