@@ -13,20 +13,25 @@ namespace tsar {
 // One warp handles 32 rows and transposes 32x32 blocks through shared memory so the table is written
 // with coalesced 128-byte rows.
 // ---------------------------------------------------------------------------------------------
+// A row is cut into segments of kRngSeg draws (blockIdx.y); a segment starts its stream at offset s*kRngSeg
+// (curand_init's third argument), so 8x more threads share the serial stepping of a C2 row.
+constexpr int kRngSeg = 416;  // multiple of 32
+
 __global__ void __launch_bounds__(32) rng_rows_kernel(uint32_t *__restrict__ table, int pitch, int H, int len,
                                                       unsigned long long seed) {
     __shared__ uint32_t tile[32][33];
     const int lane = threadIdx.x;
     const int y = blockIdx.x * 32 + lane;
+    const int seg0 = blockIdx.y * kRngSeg, seg1 = min(len, seg0 + kRngSeg);
     curandStateXORWOW_t st;
-    curand_init(seed, (unsigned long long)min(y, H - 1), 0ULL, &st);
-    for (int base = 0; base < len; base += 32) {
+    curand_init(seed, (unsigned long long)min(y, H - 1), (unsigned long long)seg0, &st);
+    for (int base = seg0; base < seg1; base += 32) {
 #pragma unroll 4
         for (int k = 0; k < 32; k++) tile[lane][k] = curand(&st);
         __syncwarp();
         for (int r = 0; r < 32; r++) {
             const int yy = blockIdx.x * 32 + r;
-            if (yy < H && base + lane < len) table[(size_t)yy * pitch + base + lane] = tile[r][lane];
+            if (yy < H && base + lane < seg1) table[(size_t)yy * pitch + base + lane] = tile[r][lane];
         }
         __syncwarp();
     }
@@ -45,7 +50,7 @@ __global__ void merge_colour_kernel(int W, int H, int colour, const float4 *__re
 }
 
 cudaError_t pm_launch_rng_table(uint32_t *table, int pitch, int H, int len, unsigned long long seed, cudaStream_t s) {
-    rng_rows_kernel<<<(H + 31) / 32, 32, 0, s>>>(table, pitch, H, len, seed);
+    rng_rows_kernel<<<dim3((H + 31) / 32, (len + kRngSeg - 1) / kRngSeg), 32, 0, s>>>(table, pitch, H, len, seed);
     return cudaGetLastError();
 }
 cudaError_t pm_launch_merge_colour(int W, int H, int colour, const float4 *psrc, const float *csrc, float4 *pdst,
