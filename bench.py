@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--blocksize", type=int, default=11, help="NCC window (the run scripts use 11; the reference's built-in default is 19)")
     return ap.parse_args()
 
 
@@ -139,9 +140,11 @@ def max_over_ranks(x, world):
     return float(t.item())
 
 
-def workload_name(cfg_name, cfg, iters):
-    return (f"{cfg_name}: synthetic ETH3D-shaped scene {cfg['W']}x{cfg['H']}, {cfg['V']} source views, one reference view per step, "
-            f"blocksize 11, {iters} iterations, n_best 1; full TSAR path (gSLICr + checkerboard PatchMatch + L/R check + "
+def workload_name(cfg_name, cfg, iters, box=11):
+    shape = {"C1": "Middlebury dinoSparseRing-shaped", "C2": "ETH3D pipes-shaped", "C4": "Tanks&Temples-shaped",
+             "C5": "full-resolution ETH3D-shaped"}.get(cfg_name, "synthetic")
+    return (f"{cfg_name}: synthetic {shape} scene {cfg['W']}x{cfg['H']}, {cfg['V']} source views, one reference view per step, "
+            f"blocksize {box}, {iters} iterations, n_best 1; full TSAR path (gSLICr + checkerboard PatchMatch + L/R check + "
             f"confidence + textureless depth completion)")
 
 
@@ -188,7 +191,7 @@ def run_ours(args):
     iters = 8
     scene, imgs_dev, imgs_host, bgrx = build_scene(pkg, args.config, rank, f"cuda:{local}")
     W, H, V = cfg["W"], cfg["H"], cfg["V"]
-    params = pkg.make_params(box=11, iterations=iters, n_best=1, cost_comb=1, min_disparity=scene["min_disparity"],
+    params = pkg.make_params(box=args.blocksize, iterations=iters, n_best=1, cost_comb=1, min_disparity=scene["min_disparity"],
                              max_disparity=scene["max_disparity"])
     # our kernels run on a torch side stream made current below, so torch.cuda.Event brackets exactly them
     tstream = torch.cuda.Stream(device=local)
@@ -215,14 +218,20 @@ def run_ours(args):
     eng.launch_count(reset=True)
     eng.profile(True)
     barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # L2 rule: C2/C5 stream far more than the 126 MB L2 per step (views + state); for the small configs a 256 MB
+    # buffer is overwritten between the timed steps, outside the per-step event pairs
+    work_bytes = (cfg["n_images"] * 5 + 72) * W * H
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}") if work_bytes < (512 << 20) else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local) as clk:
-        e0.record()
         for k in range(args.steps):
+            if flush is not None:
+                flush.fill_(k)
+            evs[k][0].record()
             step_resident(SEED + 100 * k)
-        e1.record()
+            evs[k][1].record()
         torch.cuda.synchronize()
-    ms_local = e0.elapsed_time(e1)
+    ms_local = sum(a.elapsed_time(b) for a, b in evs)
     barrier(world)
     ms = max_over_ranks(ms_local, world)
     launches = eng.launch_count(reset=True)
@@ -283,7 +292,9 @@ def run_ours(args):
     ffma_tf, mufu_g, tex_g = eng.peaks()
     evals_checker = (n_evals - V * W * H) / (2.0 * iters)           # pmCost evaluations per checkerboard launch
     avg_ms = chk_ms / max(chk_n, 1)
-    achieved = evals_checker * FLOPS_PER_EVAL / (avg_ms * 1e-3) / 1e12
+    n_samp = ((args.blocksize - 1) // 2 + 1) ** 2                   # S = (hRad + 1)^2 window samples, stride 2
+    flops_eval = 40.0 * n_samp + 150.0                              # BASELINE.md section 3 (1590 at S = 36)
+    achieved = evals_checker * flops_eval / (avg_ms * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_dram_bytes.json")
     if os.path.exists(tpath):
@@ -304,11 +315,11 @@ def run_ours(args):
         "peak_source": "FP32 FFMA issue microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry); "
                        f"nominal {FP32_NOMINAL_TFLOPS} TFLOP/s",
         "frac_of_nominal": achieved / FP32_NOMINAL_TFLOPS,
-        "algorithmic_flops_per_launch": evals_checker * FLOPS_PER_EVAL, "avg_launch_ms": avg_ms, "launches_timed": chk_n,
+        "algorithmic_flops_per_launch": evals_checker * flops_eval, "avg_launch_ms": avg_ms, "launches_timed": chk_n,
         "kernel_share_of_step": chk_ms / ms_local if ms_local else None,
         "gevals_per_s": evals_checker / (avg_ms * 1e-3) / 1e9,
-        "tex_gsamples_per_s": evals_checker * 36 / (avg_ms * 1e-3) / 1e9, "tex_peak_gsamples_per_s": tex_g,
-        "tex_frac": (evals_checker * 36 / (avg_ms * 1e-3) / 1e9) / tex_g if tex_g else None,
+        "tex_gsamples_per_s": evals_checker * n_samp / (avg_ms * 1e-3) / 1e9, "tex_peak_gsamples_per_s": tex_g,
+        "tex_frac": (evals_checker * n_samp / (avg_ms * 1e-3) / 1e9) / tex_g if tex_g else None,
         "mufu_peak_gops_measured_lower_bound": mufu_g,
         "hbm": {"bound": "hbm", "achieved": alg_bytes / (avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback"},
@@ -318,8 +329,8 @@ def run_ours(args):
         "metric": "depthmaps/s", "value": value, "unit": "depthmaps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "ours",
-        "config": {"workload": workload_name(args.config, cfg, iters), "timing": "inputs_larger_than_l2 (11 views x 25 MB + 0.4 GB state)"
-                   if args.config == "C2" else "see workload", "reference_views_per_gpu_per_step": 1, "parallelism": f"views sharded over {world} GPU(s)"},
+        "config": {"workload": workload_name(args.config, cfg, iters, args.blocksize), "timing": (f"inputs_larger_than_l2 ({work_bytes / 1e6:.0f} MB of views + state per step)" if flush is None
+                              else "l2_flush (256 MB overwritten between timed steps)"), "reference_views_per_gpu_per_step": 1, "parallelism": f"views sharded over {world} GPU(s)"},
         "gevals_per_s": world * args.steps * n_evals / (ms * 1e-3) / 1e9, "evals_per_depthmap": n_evals,
         "roofline": roofline, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
     }
@@ -359,7 +370,7 @@ def run_reference(args):
     scene, imgs_dev, imgs_host, bgrx = build_scene(pkg, args.config, 0, "cuda:0")
     from tsar_mvs_b200.engine import cameras_to_struct
     cams = cameras_to_struct(scene["cams"])
-    params = pkg.make_params(box=11, iterations=iters, n_best=1, cost_comb=1, min_disparity=scene["min_disparity"],
+    params = pkg.make_params(box=args.blocksize, iterations=iters, n_best=1, cost_comb=1, min_disparity=scene["min_disparity"],
                              max_disparity=scene["max_disparity"])
     ref = rb.RefEngine(pkg._lib.TsarCamera, pkg._lib.TsarParams, variant="asis")
     ref.create([t.numpy() for t in imgs_host], cams, scene["subset"], params, scene["cam_f"])
@@ -393,7 +404,7 @@ def run_reference(args):
         "metric": "depthmaps/s", "value": value, "unit": "depthmaps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": workload_name(args.config, cfg, iters), "note": "reference CUDA kernels rebuilt for sm_100a (gipuma.cu + gSLICr "
+        "config": {"workload": workload_name(args.config, cfg, iters, args.blocksize), "note": "reference CUDA kernels rebuilt for sm_100a (gipuma.cu + gSLICr "
                    "unmodified), managed memory, device sync after every kernel, warm (pages resident after warm-up); the reference has no CPU path"},
         "gevals_per_s": args.steps * n_evals / dt / 1e9,
         "cpu_baseline": {"value": value, "unit": "depthmaps/s", "cores": 0, "kind": "reference",
