@@ -215,6 +215,21 @@ def test_edge_cases(env):
     mine.close(); ref.close()
 
 
+def test_non_8bit_images_use_fp32_textures(env):
+    """Images that are not 8-bit valued (e.g. rescaled inputs) cannot use the 8-bit texture copies; the library
+    detects that on upload and samples the fp32 arrays like the reference: still bit-exact."""
+    pkg, rb = env
+    L = pkg._lib
+    scene = dict(pkg.scene.make_scene("tiny"))
+    scene["images"] = [(im * np.float32(0.731) + np.float32(0.2)).astype(np.float32) for im in scene["images"]]
+    params, mine, refs = pc.make_engines(pkg, scene, iterations=2, variants=("snapshot",))
+    ref = refs["snapshot"]
+    mine.depthmap(SEED); ref.depthmap(SEED, iters=2)
+    assert pc.frac_bit_exact(mine.download(L.F_NORM4), ref.download(rb.F_NORM4)) == 1.0
+    assert pc.frac_bit_exact(mine.download(L.F_CONFID), ref.download(rb.F_CONFID)) == 1.0
+    mine.close(); ref.close()
+
+
 def test_host_entry_matches_resident_path(env, small):
     """tsar_depthmap_host (host buffers in/out, the e2e path) == set_views + depthmap + download."""
     pkg, rb = env

@@ -74,10 +74,34 @@ __device__ __forceinline__ float spatial_term(int i, int j) {
     return fdiv(__fsqrt_rn((float)(i * i + j * j)), -50.0f);
 }
 
+// Where the hoisted per-sample terms of a thread live in shared memory.
+//  WPair: (w, w*ref) as one float2 per sample per thread -- [ns][NT] table, one LDS.64 per sample.
+//  WTile: w alone per sample per thread ([ns][NT] floats) + ONE reference-image tile per CTA; w*ref is re-formed by
+//         the same single multiplication.  Half the bytes per thread: what lets the 100-sample (19x19) window run
+//         3 CTAs per SM instead of 2.  Pitch 64 floats: lanes of a warp differ in column (and, on the checkerboard,
+//         by one row = 64 floats), so every access is bank-conflict free.
+template <int NT>
+struct WPair {
+    float2 *p;
+    __device__ __forceinline__ void put(int k, float w, float tr) const { p[k * NT] = make_float2(w, tr); }
+    __device__ __forceinline__ float2 get(int k, int, int) const { return p[k * NT]; }
+};
+constexpr int kTilePitch = 64;
+template <int NT>
+struct WTile {
+    float *w;
+    const float *rt;  // tile element of the thread's window origin (x - hrad, y - vrad)
+    __device__ __forceinline__ void put(int k, float wv, float) const { w[k * NT] = wv; }
+    __device__ __forceinline__ float2 get(int k, int ii, int jj) const {
+        const float wv = w[k * NT];
+        return make_float2(wv, fmul(rt[2 * jj * kTilePitch + 2 * ii], wv));
+    }
+};
+
 // N1 = samples per axis known at compile time (hRad+1, square window) or 0 for run-time sizes.
-template <int NT, int N1>
+template <int NT, int N1, class WS>
 __device__ __forceinline__ RefStats window_weights(const PmConst &c, const float *__restrict__ ref, int x, int y,
-                                                   const float *__restrict__ sp, float2 *__restrict__ wt_thread) {
+                                                   const float *__restrict__ sp, const WS &ws) {
     const int W = c.W, H = c.H;
     // tex2D(l, x+0.5, y+0.5) with unnormalised coords: clamp addressing, exact texel
     const int xc = min(max(x, 0), W - 1), yc = min(max(y, 0), H - 1);
@@ -100,7 +124,7 @@ __device__ __forceinline__ RefStats window_weights(const PmConst &c, const float
             sum_ref = fadd(sum_ref, tr);       // gipuma.cu:270
             sum_rr = ffma(r, tr, sum_rr);      // gipuma.cu:271
             wsum = fadd(wsum, w);              // gipuma.cu:275
-            wt_thread[k * NT] = make_float2(w, tr);
+            ws.put(k, w, tr);
         }
     }
     RefStats s;
@@ -161,9 +185,9 @@ __device__ __forceinline__ void homography(const PmConst &c, const ViewC &v, con
 // window sums are carried in units of N (i.e. scaled by 2^8 / 2^16, exact in binary floating point) and
 // scaled back once per evaluation, so costs are bit-identical to the fp32-texture path while each warp-wide
 // fetch moves a quarter of the texel bytes through the L1TEX data pipe (the measured limiter).
-template <int NT, int N1, bool PXF, bool U8>
+template <int NT, int N1, bool PXF, bool U8, class WS>
 __device__ __forceinline__ float view_cost(const PmConst &c, int vi, int x, int y, const float4 &pl,
-                                           const float2 *__restrict__ wt_thread, const RefStats &rs) {
+                                           const WS &ws, const RefStats &rs) {
     float Hm[9];
     homography(c, c.view[vi], pl, Hm);
     const cudaTextureObject_t tex = U8 ? c.tex8[vi] : c.tex[vi];
@@ -208,7 +232,7 @@ __device__ __forceinline__ float view_cost(const PmConst &c, int vi, int x, int 
                 const float ys_ = fadd(div_refined(Y, Z, r), 0.5f);
                 float src = tex2D<float>(tex, xs_, ys_);  // hardware bilinear, clamp
                 if (U8) src = fsub(ffma(src, 65280.0f, 12582912.0f), 12582912.0f);  // N = rint(v * 255 * 256)
-                const float2 w = wt_thread[k * NT];            // (w, w*ref)
+                const float2 w = ws.get(k, ii, jj);            // (w, w*ref)
                 const float ts = fmul(src, w.x);
                 s_s = fadd(s_s, ts);            // gipuma.cu:272
                 s_ss = ffma(src, ts, s_ss);     // :273
@@ -228,7 +252,7 @@ __device__ __forceinline__ float view_cost(const PmConst &c, int vi, int x, int 
                 const float Z = fadd(Hm[8], PXF ? ffma(Hm[7], py, a2) : ffma(Hm[6], px, fmul(Hm[7], py)));
                 float src = tex2D<float>(tex, fadd(fdiv(X, Z), 0.5f), fadd(fdiv(Y, Z), 0.5f));
                 if (U8) src = fsub(ffma(src, 65280.0f, 12582912.0f), 12582912.0f);
-                const float2 w = wt_thread[k * NT];
+                const float2 w = ws.get(k, ii, jj);
                 const float ts = fmul(src, w.x);
                 s_s = fadd(s_s, ts);
                 s_ss = ffma(src, ts, s_ss);
@@ -258,15 +282,15 @@ struct MvResult {
 // GENERIC = false: only the two smallest costs are ever read (cost_comb == COMB_BEST_N and
 // n_best <= 2, the setting of every run script), kept in registers.  GENERIC = true: any n_best /
 // COMB_ALL through the reference's full insertion sort (local-memory arrays, as the reference).
-template <int NT, int N1, bool GENERIC, bool PXF = false, bool U8 = false>
+template <int NT, int N1, bool GENERIC, bool PXF = false, bool U8 = false, class WS = WPair<NT>>
 __device__ __forceinline__ MvResult multiview_cost(const PmConst &c, int x, int y, const float4 &pl,
-                                                   const float2 *__restrict__ wt_thread, const RefStats &rs) {
+                                                   const WS &ws, const RefStats &rs) {
     MvResult out;
     if (!GENERIC) {
         float s0 = __int_as_float(0x7f800000), s1 = __int_as_float(0x7f800000);
         int nvalid = 0, bidx = -1;
         for (int vi = 0; vi < c.V; vi++) {
-            float cv = view_cost<NT, N1, PXF, U8>(c, vi, x, y, pl, wt_thread, rs);
+            float cv = view_cost<NT, N1, PXF, U8>(c, vi, x, y, pl, ws, rs);
             if (cv < kMaxCost) nvalid++;
             else cv = kMaxCost;
             if (cv < s0) { s1 = s0; s0 = cv; bidx = vi; }
@@ -289,7 +313,7 @@ __device__ __forceinline__ MvResult multiview_cost(const PmConst &c, int x, int 
         float cv[kMaxViews], orig[kMaxViews];
         int nvalid = 0;
         for (int vi = 0; vi < c.V; vi++) {
-            float v = view_cost<NT, N1, PXF, U8>(c, vi, x, y, pl, wt_thread, rs);
+            float v = view_cost<NT, N1, PXF, U8>(c, vi, x, y, pl, ws, rs);
             if (v < kMaxCost) nvalid++;
             else v = kMaxCost;
             cv[vi] = v; orig[vi] = v;

@@ -1,8 +1,10 @@
-// 19x19 window (AlgorithmParameters default, algorithmparameters.h:25-26): 100 samples, 128-thread CTAs
+// 19x19 window (AlgorithmParameters default, algorithmparameters.h:25-26): 100 samples, 128-thread CTAs;
+// checkerboard kernel: w per thread + one reference tile per CTA (60 KB) -> 3 CTAs per SM instead of 2
 #define PM_VARIANT pm_variant_w19
 #define PM_LABEL "w19"
 #define PM_NT 128
-#define PM_MINB 2
+#define PM_MINB 3
+#define PM_TILE 1
 #define PM_N1 10
 #define PM_GEN false
 #include "pm_inst.inc"

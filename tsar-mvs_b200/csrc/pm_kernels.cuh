@@ -1,6 +1,8 @@
 // pm_kernels.cuh -- __global__ kernels of the PatchMatch path (random init, checkerboard propagation,
 // plane refinement, explicit-plane evaluation, XORWOW row tables).  Instantiated per window variant by pm_inst_*.cu.
 #pragma once
+#include <type_traits>
+
 #include "pm_core.cuh"
 #include "pm_launch.h"
 
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_init_kernel(const __grid_constant
     __syncthreads();
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= c.W || y >= c.H) return;
-    float2 *wt = sm.wt + tid;
+    const WPair<NT> wt{sm.wt + tid};
     const RefStats rs = window_weights<NT, N1>(c, ref, x, y, sm.sp, wt);
 
     const uint32_t *row = rng + (size_t)y * c.rng_pitch + x;
@@ -81,15 +83,30 @@ __global__ void __launch_bounds__(NT, MINB) pm_init_kernel(const __grid_constant
 // colours), the thread's own result goes to `*_out` (which may alias `*_in` when DO_SP is false).
 // ---------------------------------------------------------------------------------------------
 
-template <int NT, int MINB, int N1, bool GEN, bool U8, bool DO_SP, bool DO_PR>
+template <int NT, int MINB, int N1, bool GEN, bool U8, bool DO_SP, bool DO_PR, bool TILE>
 __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_constant__ PmConst c,
                                                         const float *__restrict__ ref, const CheckerArgs a) {
+    static_assert(!TILE || N1 > 0, "the tile layout needs a compile-time window");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WinSmem<NT> sm(smem_raw, N1 ? N1 * N1 : c.ns);
+    WinSmem<NT> sm(smem_raw, N1 ? N1 * N1 : c.ns);   // (TILE: the table holds floats, see checker_smem_bytes)
     const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int W = c.W, H = c.H;
+    float *tile = nullptr;
+    if (TILE) {
+        // reference-image tile of the CTA: 32 + 2*hrad columns x 2*(NT/32) + 2*vrad rows, clamp addressing applied
+        // while loading (same coordinate clamp as the window loop of window_weights)
+        constexpr int HR = N1 - 1, TW = 32 + 2 * HR, TH = 2 * (NT / 32) + 2 * HR;
+        float *wtab = reinterpret_cast<float *>(smem_raw);
+        sm.sp = wtab + N1 * N1 * NT;
+        tile = sm.sp + N1 * N1;
+        const int x0 = blockIdx.x * 32 - HR, y0 = blockIdx.y * (NT / 32) * 2 - HR;
+        for (int idx = tid; idx < kTilePitch * TH; idx += NT) {
+            const int tx = idx % kTilePitch, ty = idx / kTilePitch;
+            if (tx < TW) tile[idx] = __ldg(ref + (size_t)min(max(y0 + ty, 0), H - 1) * W + min(max(x0 + tx, 0), W - 1));
+        }
+    }
     fill_spatial_table<N1>(c, sm.sp, tid, NT);
     __syncthreads();
-    const int W = c.W, H = c.H;
     // block = 32 columns x (NT/32) row pairs; lane parity selects the row of the pair exactly as the reference's
     // wrappers do (gipuma.cu:1099-1103).  (More compact warp footprints were measured: no difference.)
     const int x = blockIdx.x * 32 + threadIdx.x;
@@ -98,7 +115,14 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
     const int own = a.colour;
     const int pidx = y * W + x;
 
-    float2 *wt = sm.wt + tid;
+    using WS = typename std::conditional<TILE, WTile<NT>, WPair<NT>>::type;
+    WS wt;
+    if constexpr (TILE) {
+        wt.w = reinterpret_cast<float *>(smem_raw) + tid;
+        wt.rt = tile + (y - (int)blockIdx.y * (NT / 32) * 2) * kTilePitch + threadIdx.x;
+    } else {
+        wt.p = sm.wt + tid;
+    }
     const RefStats rs = window_weights<NT, N1>(c, ref, x, y, sm.sp, wt);
 
     // (no dynamic indexing into the by-value argument struct: that would force a local-memory copy)
@@ -274,7 +298,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_eval_kernel(const __grid_constant
     const int i = blockIdx.x * NT + tid;
     if (i >= n) return;
     const int2 p = xy[i];
-    float2 *wt = sm.wt + tid;
+    const WPair<NT> wt{sm.wt + tid};
     const RefStats rs = window_weights<NT, N1>(c, ref, p.x, p.y, sm.sp, wt);
     const MvResult r = multiview_cost<NT, N1, GEN, PXF, U8>(c, p.x, p.y, planes[i], wt, rs);
     cost[i] = r.cost;
@@ -295,7 +319,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_cost_of_state_kernel(const __grid
     __syncthreads();
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= c.W || y >= c.H) return;
-    float2 *wt = sm.wt + tid;
+    const WPair<NT> wt{sm.wt + tid};
     const RefStats rs = window_weights<NT, N1>(c, ref, x, y, sm.sp, wt);
     const size_t p = (size_t)y * c.W + x;
     cost[p] = multiview_cost<NT, N1, GEN, false, U8>(c, x, y, plane[p], wt, rs).cost;
