@@ -54,8 +54,8 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc, self.th = index, [], None, None
+    def __init__(self, index, enabled=True):
+        self.index, self.rows, self.proc, self.th, self.enabled = index, [], None, None, enabled
 
     def _run(self):
         for line in self.proc.stdout:
@@ -64,6 +64,8 @@ class ClockSampler:
                 self.rows.append(cols)
 
     def __enter__(self):
+        if not self.enabled:       # only rank 0 reports clocks; 8 pollers on one node would only add noise
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -223,7 +225,7 @@ def run_ours(args):
     work_bytes = (cfg["n_images"] * 5 + 72) * W * H
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}") if work_bytes < (512 << 20) else None
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
         for k in range(args.steps):
             if flush is not None:
                 flush.fill_(k)
