@@ -754,13 +754,21 @@ int tsar_fit_region_planes(tsar_ctx *ctx, int n_regions, const float *region_tex
     uint32_t *d_rnd = nullptr;
     RansacJob *d_jobs = nullptr;
     float4 *d_out = nullptr;
+    RansacState *d_state = nullptr;
+    int *d_hyp_counts = nullptr, *d_cursors = nullptr;
     std::vector<RansacJob> jobs(nt);
-    auto cleanup = [&]() { cudaFree(d_counts); cudaFree(d_list); cudaFree(d_total); cudaFree(d_pts); cudaFree(d_rnd); cudaFree(d_jobs); cudaFree(d_out); };
+    auto cleanup = [&]() {
+        cudaFree(d_counts); cudaFree(d_list); cudaFree(d_total); cudaFree(d_pts); cudaFree(d_rnd); cudaFree(d_jobs); cudaFree(d_out);
+        cudaFree(d_state); cudaFree(d_hyp_counts); cudaFree(d_cursors);
+    };
 #define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); ctx->err = std::string(#call ": ") + cudaGetErrorString(e_); return TSAR_ERR_CUDA; } } while (0)
     CKF(cudaMalloc(&d_counts, (size_t)nb * 4)); CKF(cudaMalloc(&d_list, (size_t)n * 4)); CKF(cudaMalloc(&d_total, 4));
     CKF(cudaMalloc(&d_pts, (size_t)nt * kRansacMaxPts * sizeof(float3)));
     CKF(cudaMalloc(&d_rnd, (size_t)nt * kRansacRandPerRegion * 4));
     CKF(cudaMalloc(&d_jobs, (size_t)nt * sizeof(RansacJob))); CKF(cudaMalloc(&d_out, (size_t)nt * sizeof(float4)));
+    CKF(cudaMalloc(&d_state, (size_t)nt * sizeof(RansacState))); CKF(cudaMalloc(&d_cursors, (size_t)nt * 4));
+    CKF(cudaMalloc(&d_hyp_counts, (size_t)nt * kRansacBatch * 4));
+    CKF(cudaMemsetAsync(d_hyp_counts, 0, (size_t)nt * kRansacBatch * 4, ctx->stream));
     for (int t = 0; t < nt; t++) {
         const int r = targets[t];
         ransac_flag_kernel<<<nb, 1024, 0, ctx->stream>>>(ctx->scale, ctx->canny, n, r, d_counts);
@@ -782,9 +790,37 @@ int tsar_fit_region_planes(tsar_ctx *ctx, int n_regions, const float *region_tex
     for (int t = 0; t < nt; t++) out[t] = make_float4(region_norm4[4 * targets[t]], region_norm4[4 * targets[t] + 1], region_norm4[4 * targets[t] + 2], region_norm4[4 * targets[t] + 3]);
     CKF(cudaMemcpyAsync(d_out, out.data(), (size_t)nt * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CKF(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nt * sizeof(RansacJob), cudaMemcpyHostToDevice, ctx->stream));
-    ransac_fit_kernel<<<nt, 1024, 0, ctx->stream>>>(d_jobs);
-    ctx->launches++;
-    CKF(cudaGetLastError());
+    int max_n = 0;
+    for (int t = 0; t < nt; t++) max_n = std::max(max_n, jobs[t].n);
+    if (max_n > 0) {
+        const dim3 cgrid((max_n + 255) / 256, nt);
+        ransac_state_init_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(d_jobs, d_state, nt);
+        ctx->launches++;
+        // RANSAC hypotheses: the inlier threshold is constant between hypotheses 1000 j and 1000 (j+1)
+        for (int first = 0; first < kRansacIters;) {
+            const int count = first == 0 ? 1 : std::min(kRansacBatch, kRansacIters - first);
+            ransac_batch_count_kernel<<<cgrid, 256, 0, ctx->stream>>>(d_jobs, d_state, 0, first, count, d_hyp_counts);
+            ransac_select_kernel<<<nt, 1024, 0, ctx->stream>>>(d_jobs, d_state, 0, first, count, d_hyp_counts, d_cursors);
+            ctx->launches += 2;
+            first += count;
+        }
+        CKF(cudaGetLastError());
+        // local refinement: every trial perturbs the CURRENT best, so trials are evaluated speculatively in batches
+        // and the first accepted one is committed; the host only reads the cursors back
+        std::vector<int> cursors(nt, 0);
+        const int spec = 256;
+        for (int guard = 0; guard <= kRefineTotal; guard++) {
+            ransac_batch_count_kernel<<<cgrid, 256, 0, ctx->stream>>>(d_jobs, d_state, 1, 0, spec, d_hyp_counts);
+            ransac_select_kernel<<<nt, 1024, 0, ctx->stream>>>(d_jobs, d_state, 1, 0, spec, d_hyp_counts, d_cursors);
+            ctx->launches += 2;
+            CKF(cudaMemcpyAsync(cursors.data(), d_cursors, (size_t)nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CKF(cudaStreamSynchronize(ctx->stream));
+            bool done = true;
+            for (int t = 0; t < nt; t++) done = done && cursors[t] >= kRefineTotal;
+            if (done) break;
+        }
+        CKF(cudaGetLastError());
+    }
     CKF(cudaMemcpyAsync(out.data(), d_out, (size_t)nt * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     CKF(cudaStreamSynchronize(ctx->stream));
 #undef CKF

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
         float *wtab = reinterpret_cast<float *>(smem_raw);
         sm.sp = wtab + N1 * N1 * NT;
         tile = sm.sp + N1 * N1;
-        const int x0 = blockIdx.x * 32 - HR, y0 = blockIdx.y * (NT / 32) * 2 - HR;
+        const int x0 = (int)blockIdx.x * 32 - HR, y0 = (int)blockIdx.y * (NT / 32) * 2 - HR;
         for (int idx = tid; idx < kTilePitch * TH; idx += NT) {
             const int tx = idx % kTilePitch, ty = idx / kTilePitch;
             if (tx < TW) tile[idx] = __ldg(ref + (size_t)min(max(y0 + ty, 0), H - 1) * W + min(max(x0 + tx, 0), W - 1));

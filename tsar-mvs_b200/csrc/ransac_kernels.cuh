@@ -5,8 +5,9 @@
 // about 7e8 double residuals per region on one CPU core in the reference.
 //
 // Here: device-side stable compaction of the region's reliable pixels (raster order, as the reference collects
-// them), back-projection, and one persistent 1024-thread CTA per region that evaluates every hypothesis with a
-// block-wide inlier count.  All arithmetic is IEEE double without contraction, in the reference's evaluation
+// them), back-projection, then batches of hypotheses counted by the whole GPU (ransac_batch_count_kernel: a CTA owns
+// 256 points and runs through the batch) with the loop-carried part -- best-so-far, adaptive threshold, commit of the
+// first accepted perturbation -- in a one-CTA-per-region kernel between the batches (ransac_select_kernel).  All arithmetic is IEEE double without contraction, in the reference's evaluation
 // order, so the result is bit-identical to a scalar C restatement given the same random numbers.  The reference
 // draws them from rand()/system_clock (not reproducible); the caller supplies the stream instead (the values
 // rand() would have returned, 46 000 per region), which also makes the fit testable.
@@ -131,54 +132,157 @@ struct RansacJob {
     float4 *out;         // cannylines->norm4[region]
 };
 
-__global__ void __launch_bounds__(1024) ransac_fit_kernel(const RansacJob *__restrict__ jobs) {
+// Running state of one region's fit (the reference's loop-carried variables, main.cpp:1600-1710)
+struct RansacState {
+    double a, b, c, d, maximum;
+    float depth_abs;
+    int cursor;          // refinement phase: index (0..3999) of the next perturbation to try
+};
+
+constexpr int kRansacBatch = 1000;   // hypotheses evaluated per launch (the threshold only changes every 1000)
+constexpr int kRefineTotal = 4 * kRefineRounds;
+
+// plane of RANSAC hypothesis k (calcLinePara main.cpp:147-164 incl. its A coefficient as written, then the
+// normalisation of main.cpp:1621-1626)
+__device__ __forceinline__ void ransac_triple_plane(const RansacJob &job, int k, double &ta, double &tb, double &tc, double &td) {
+    const uint32_t n = (uint32_t)job.n;
+    const float3 P1 = job.pts[job.rnd[3 * k] % n], P2 = job.pts[job.rnd[3 * k + 1] % n], P3 = job.pts[job.rnd[3 * k + 2] % n];
+    const double x1 = P1.x, y1 = P1.y, z1 = P1.z, x2 = P2.x, y2 = P2.y, z2 = P2.z, x3 = P3.x, y3 = P3.y, z3 = P3.z;
+    ta = dadd(dmul(dadd(y3, -y1), dadd(z3, -z1)), -dmul(dadd(z2, -z1), dadd(y3, -y1)));
+    tb = dadd(dmul(dadd(x3, -x1), dadd(z2, -z1)), -dmul(dadd(x2, -x1), dadd(z3, -z1)));
+    tc = dadd(dmul(dadd(x2, -x1), dadd(y3, -y1)), -dmul(dadd(x3, -x1), dadd(y2, -y1)));
+    td = -dadd(dadd(dmul(ta, x1), dmul(tb, y1)), dmul(tc, z1));
+    const double sq = __dsqrt_rn(dadd(dadd(dmul(ta, ta), dmul(tb, tb)), dmul(tc, tc)));
+    ta = __ddiv_rn(ta, sq); tb = __ddiv_rn(tb, sq); tc = __ddiv_rn(tc, sq); td = __ddiv_rn(td, sq);
+}
+
+// plane of refinement trial q (0..3999) around the current best (main.cpp:1668-1700): round q/4, scale j =
+// 2000, 200, 20, 2 for q%4 = 0..3, four rand() values each
+__device__ __forceinline__ void ransac_perturbed_plane(const RansacJob &job, const RansacState &st, int q, double &ra, double &rb,
+                                                       double &rc, double &rd) {
+    const uint32_t *rr = job.rnd + 3 * kRansacIters + 4 * q;
+    const int m = q & 3;
+    const int j = m == 0 ? 2000 : (m == 1 ? 200 : (m == 2 ? 20 : 2));
+    const int med = j / 2;
+    const double da = (double)((int)(rr[0] % (uint32_t)j) - med) / 10000.0, db = (double)((int)(rr[1] % (uint32_t)j) - med) / 10000.0;
+    const double dc = (double)((int)(rr[2] % (uint32_t)j) - med) / 10000.0, dd = (double)((int)(rr[3] % (uint32_t)j) - med) / 1000.0;
+    ra = dadd(st.a, da); rb = dadd(st.b, db); rc = dadd(st.c, dc); rd = dadd(st.d, dd);
+    const double sq = __dsqrt_rn(dadd(dadd(dmul(ra, ra), dmul(rb, rb)), dmul(rc, rc)));
+    ra = __ddiv_rn(ra, sq); rb = __ddiv_rn(rb, sq); rc = __ddiv_rn(rc, sq); rd = __ddiv_rn(rd, sq);
+}
+
+__global__ void ransac_state_init_kernel(const RansacJob *__restrict__ jobs, RansacState *__restrict__ st, int n_jobs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_jobs) return;
+    RansacState s;
+    s.a = 0; s.b = 0; s.c = 1; s.d = -1; s.maximum = 0;
+    s.depth_abs = (float)(0.0003 * (double)sqrtf(jobs[r].size / 20.0f));  // main.cpp:1552-1553
+    s.cursor = 0;
+    st[r] = s;
+}
+
+// Inlier counts of a batch of hypotheses.  grid = (point slices of 256, regions): a CTA keeps ITS 256 points in
+// registers (as doubles) and runs through all hypotheses of the batch, whose plane parameters every CTA computes
+// redundantly into shared memory (cheap: 60 flops per hypothesis versus 8 per point x hypothesis).  So the points
+// are read once per launch, the planes are shared-memory broadcasts, and the work of one region spreads over
+// n/256 CTAs instead of one.  refine = 0: RANSAC hypotheses first .. first+count-1; refine = 1: perturbation trials
+// cursor .. cursor+count-1 of the current best.
+__global__ void __launch_bounds__(256) ransac_batch_count_kernel(const RansacJob *__restrict__ jobs, const RansacState *__restrict__ states,
+                                                                 int refine, int first, int count, int *__restrict__ counts) {
+    __shared__ double pa[kRansacBatch], pb[kRansacBatch], pc[kRansacBatch], pd[kRansacBatch];
+    __shared__ int cnt_s[kRansacBatch];
+    const RansacJob job = jobs[blockIdx.y];
+    const RansacState st = states[blockIdx.y];
+    const int n = job.n;
+    if (n <= 0 || (int)blockIdx.x * 256 >= n) return;
+    if (refine) {
+        first = st.cursor;
+        count = min(count, kRefineTotal - first);
+        if (count <= 0) return;
+    }
+    for (int h = threadIdx.x; h < count; h += 256) {
+        double a, b, c, d;
+        if (refine) ransac_perturbed_plane(job, st, first + h, a, b, c, d);
+        else ransac_triple_plane(job, first + h, a, b, c, d);
+        pa[h] = a; pb[h] = b; pc[h] = c; pd[h] = d;
+        cnt_s[h] = 0;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const bool valid = i < n;
+    const float3 p = job.pts[valid ? i : 0];
+    const double x = p.x, y = p.y, z = p.z, thr = (double)st.depth_abs;
+    const int lane = threadIdx.x & 31;
+    for (int h = 0; h < count; h++) {
+        const double r = fabs(dadd(dadd(dadd(dmul(x, pa[h]), dmul(y, pb[h])), dmul(z, pc[h])), pd[h]));
+        const unsigned bal = __ballot_sync(0xffffffffu, valid && r < thr);
+        if (lane == 0 && bal) atomicAdd(&cnt_s[h], __popc(bal));
+    }
+    __syncthreads();
+    int *out = counts + (size_t)blockIdx.y * kRansacBatch;
+    for (int h = threadIdx.x; h < count; h += 256)
+        if (cnt_s[h]) atomicAdd(&out[h], cnt_s[h]);
+}
+
+// Sequential part, one CTA per region: walks the batch's counts in hypothesis order with the reference's
+// acceptance rule (>= replaces the best), applies the adaptive inlier threshold after hypotheses 0, 1000, 2000, ...
+// (main.cpp:1645-1663), or -- refinement -- commits the FIRST accepted perturbation and moves the cursor behind it
+// (later trials of the batch were perturbations of the old best and are evaluated again from the new one).
+__global__ void __launch_bounds__(1024) ransac_select_kernel(const RansacJob *__restrict__ jobs, RansacState *__restrict__ states,
+                                                             int refine, int first, int count, int *__restrict__ counts,
+                                                             int *__restrict__ cursors) {
     __shared__ int smem_counts[32];
+    __shared__ RansacState sst;
     const RansacJob job = jobs[blockIdx.x];
     const int n = job.n;
-    if (n <= 0) return;
-    const float3 *pts = job.pts;
-    const uint32_t *rnd = job.rnd;
-    float depth_abs = (float)(0.0003 * (double)sqrtf(job.size / 20.0f));  // main.cpp:1552-1553
-    double a = 0, b = 0, c = 1, d = -1, maximum = 0;
-    for (int k = 0; k < kRansacIters; k++) {
-        const float3 P1 = pts[rnd[3 * k] % (uint32_t)n], P2 = pts[rnd[3 * k + 1] % (uint32_t)n], P3 = pts[rnd[3 * k + 2] % (uint32_t)n];
-        const double x1 = P1.x, y1 = P1.y, z1 = P1.z, x2 = P2.x, y2 = P2.y, z2 = P2.z, x3 = P3.x, y3 = P3.y, z3 = P3.z;
-        // calcLinePara (main.cpp:147-164), including its A coefficient as written
-        double ta = dadd(dmul(dadd(y3, -y1), dadd(z3, -z1)), -dmul(dadd(z2, -z1), dadd(y3, -y1)));
-        double tb = dadd(dmul(dadd(x3, -x1), dadd(z2, -z1)), -dmul(dadd(x2, -x1), dadd(z3, -z1)));
-        double tc = dadd(dmul(dadd(x2, -x1), dadd(y3, -y1)), -dmul(dadd(x3, -x1), dadd(y2, -y1)));
-        double td = -dadd(dadd(dmul(ta, x1), dmul(tb, y1)), dmul(tc, z1));
-        const double sq = __dsqrt_rn(dadd(dadd(dmul(ta, ta), dmul(tb, tb)), dmul(tc, tc)));
-        ta = __ddiv_rn(ta, sq); tb = __ddiv_rn(tb, sq); tc = __ddiv_rn(tc, sq); td = __ddiv_rn(td, sq);
-        const double cnt = (double)ransac_count(pts, n, ta, tb, tc, td, (double)depth_abs, smem_counts);
-        if (cnt >= maximum) { a = ta; b = tb; c = tc; d = td; maximum = cnt; }
-        if (k % 1000 == 0) {  // adaptive threshold, main.cpp:1645-1663
-            const double rat = maximum / (double)n;
-            if (rat < 0.3 && (double)depth_abs < 0.003) {
-                depth_abs = (float)((double)depth_abs + 0.0001);
+    int *cnt = counts + (size_t)blockIdx.x * kRansacBatch;
+    if (n <= 0) { if (threadIdx.x == 0) cursors[blockIdx.x] = kRefineTotal; return; }
+    if (threadIdx.x == 0) {
+        RansacState st = states[blockIdx.x];
+        if (!refine) {
+            int best = -1;
+            for (int h = 0; h < count; h++)
+                if ((double)cnt[h] >= st.maximum) { st.maximum = (double)cnt[h]; best = h; }
+            if (best >= 0) ransac_triple_plane(job, first + best, st.a, st.b, st.c, st.d);
+        } else {
+            const int base = st.cursor, m = min(count, kRefineTotal - base);
+            int hit = -1;
+            for (int h = 0; h < m; h++)
+                if ((double)cnt[h] >= st.maximum) { hit = h; break; }
+            if (hit >= 0) {
+                double a, b, c, d;
+                ransac_perturbed_plane(job, st, base + hit, a, b, c, d);
+                st.a = a; st.b = b; st.c = c; st.d = d; st.maximum = (double)cnt[hit];
+                st.cursor = base + hit + 1;
             } else {
-                const double m2 = (double)ransac_count(pts, n, a, b, c, d, dadd((double)depth_abs, 0.0001), smem_counts);
-                if (m2 > dadd(maximum, dmul((double)n, 0.02))) {
-                    depth_abs = (float)((double)depth_abs + 0.0001);
-                    maximum = m2;
-                }
+                st.cursor = base + max(m, 0);
+            }
+            cursors[blockIdx.x] = st.cursor;
+        }
+        sst = st;
+    }
+    __syncthreads();
+    // the adaptive threshold step follows hypothesis k whenever k % 1000 == 0; batches end exactly there
+    if (!refine && ((first + count - 1) % 1000) == 0) {
+        const double rat = sst.maximum / (double)n;
+        if (rat < 0.3 && (double)sst.depth_abs < 0.003) {
+            __syncthreads();
+            if (threadIdx.x == 0) sst.depth_abs = (float)((double)sst.depth_abs + 0.0001);
+        } else {
+            const double m2 = (double)ransac_count(job.pts, n, sst.a, sst.b, sst.c, sst.d, dadd((double)sst.depth_abs, 0.0001), smem_counts);
+            __syncthreads();
+            if (threadIdx.x == 0 && m2 > dadd(sst.maximum, dmul((double)n, 0.02))) {
+                sst.depth_abs = (float)((double)sst.depth_abs + 0.0001);
+                sst.maximum = m2;
             }
         }
+        __syncthreads();
     }
-    const uint32_t *rr = rnd + 3 * kRansacIters;
-    for (int i = 0; i < kRefineRounds; i++)  // main.cpp:1668-1710
-        for (int j = 2000; j >= 2; j /= 10) {
-            const int med = j / 2;
-            const double da = (double)((int)(rr[0] % (uint32_t)j) - med) / 10000.0, db = (double)((int)(rr[1] % (uint32_t)j) - med) / 10000.0;
-            const double dc = (double)((int)(rr[2] % (uint32_t)j) - med) / 10000.0, dd = (double)((int)(rr[3] % (uint32_t)j) - med) / 1000.0;
-            rr += 4;
-            double ra = dadd(a, da), rb = dadd(b, db), rc = dadd(c, dc), rd = dadd(d, dd);
-            const double sq = __dsqrt_rn(dadd(dadd(dmul(ra, ra), dmul(rb, rb)), dmul(rc, rc)));
-            ra = __ddiv_rn(ra, sq); rb = __ddiv_rn(rb, sq); rc = __ddiv_rn(rc, sq); rd = __ddiv_rn(rd, sq);
-            const double cnt = (double)ransac_count(pts, n, ra, rb, rc, rd, (double)depth_abs, smem_counts);
-            if (cnt >= maximum) { a = ra; b = rb; c = rc; d = rd; maximum = cnt; }
-        }
-    if (threadIdx.x == 0) *job.out = make_float4((float)a, (float)b, (float)c, (float)d);
+    if (threadIdx.x == 0) {
+        states[blockIdx.x] = sst;
+        *job.out = make_float4((float)sst.a, (float)sst.b, (float)sst.c, (float)sst.d);
+    }
+    for (int h = threadIdx.x; h < kRansacBatch; h += blockDim.x) cnt[h] = 0;
 }
 
 }  // namespace tsar
