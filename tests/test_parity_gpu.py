@@ -396,6 +396,38 @@ def test_wmf_and_wmf_final_bit_exact(env, small):
     mine.close(); ref.close()
 
 
+def test_wmf_cooperative_equals_per_thread(env, monkeypatch):
+    """The warp-cooperative gipuma_WMF (bitonic sort of (key, slot) composites, sequential sums by one lane) and the
+    per-thread implementation (merge sort in local memory) give identical flags on every level, on an image with
+    borders, unreliable areas and ties (propagated planes are exact copies)."""
+    pkg, rb = env
+    L = pkg._lib
+    cfg = dict(W=333, H=201, n_images=3, V=2, fx=400.0, radius=2.0, arc_deg=12.0)
+    scene = pkg.scene.make_scene(cfg)
+    params, mine, _ = pc.make_engines(pkg, scene, iterations=2, variants=())
+    mine.depthmap(SEED)
+    mine.init_planes(SEED); mine.iterate(2, SEED); mine.lrdiff(); mine.getview()
+    cost = mine.download(L.F_COST)
+    rng = np.random.RandomState(4)
+    reliable = ((cost < 0.3) & (rng.rand(*cost.shape) < 0.9)).astype(np.float32)
+    reliable[:, :40] = 0                                   # a band with (almost) no reliable neighbours
+    reliable[60:64, 100:104] = 1
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("TSAR_B200_WMF_PER_THREAD", mode)
+        mine.upload(L.F_SCALE, reliable)
+        levels = []
+        for it in range(4):
+            mine.wmf(it)
+            levels.append(mine.download(L.F_SCALE).copy())
+        outs[mode] = levels
+    monkeypatch.delenv("TSAR_B200_WMF_PER_THREAD")
+    mine.close()
+    for it in range(4):
+        assert np.array_equal(outs["0"][it], outs["1"][it]), (it, float((outs["0"][it] != outs["1"][it]).mean()))
+    assert 0.05 < outs["0"][3].mean() < 0.999
+
+
 def test_region_plane_fit_matches_restatement(env, small):
     """Per-region RANSAC plane fit (main.cpp:1520-1730) -- the reference's host program cannot be built here (OpenCV,
     Windows), so the checker is the scalar C restatement (oracle/oracle_cpu.c) fed with the same random stream;

@@ -682,7 +682,9 @@ int tsar_wmf(tsar_ctx *ctx, int iter) {
     if ((rc = consolidate(ctx))) return rc;
     const size_t npx = (size_t)ctx->W * ctx->H;
     if ((rc = ensure_scratch(ctx, npx * 4))) return rc;
-    rc = wmf_launch(ctx->glue, ctx->ref_img, ctx->plane[0], ctx->depth, ctx->scale, (float *)ctx->scratch, iter, ctx->stream);
+    const char *pt = getenv("TSAR_B200_WMF_PER_THREAD");
+    rc = wmf_launch(ctx->glue, ctx->ref_img, ctx->plane[0], ctx->depth, ctx->scale, (float *)ctx->scratch, iter, pt && pt[0] == '1',
+                    ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     return rc;

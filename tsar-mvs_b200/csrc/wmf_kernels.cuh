@@ -7,9 +7,9 @@
 //     neighbour): effectively num+1 elements are sorted -- a dummy (value 0, weight 0, index 0)
 //     takes part, and the LARGEST element ends at position num, outside every later `i < num` loop;
 //   * the sort is stable (`>` comparison), sums run in sorted order.
-// Instead of sorting (O(n^2) swaps of local-memory arrays, four times) the sorted sequence is generated on
-// the fly by repeated stable min-extraction with a 128-bit "used" mask, and only as far as each weighted
-// median needs; the only full pass is the depth order (its weights feed wSum in sorted order).
+// Instead of bubble-sorting (O(n^2) swaps of local-memory arrays, four times) each key is ordered by a per-thread
+// stable merge sort of (key, position) composites, O(n log n); sums then run over that order sequentially, as the
+// reference's do.
 // The reference also races here (a launch reads scale/depth/norm4 of neighbours while other threads rewrite
 // them); as for the propagation kernel we read a pre-launch snapshot (the caller passes *_in copies).
 #pragma once
@@ -25,26 +25,44 @@ struct WmfList {
     int num;
 };
 
-// position-ordered stable extraction: returns the element with the smallest key among the unused ones
-// (ties: lowest original index), marks it used.  m = num + 1 elements.
-__device__ __forceinline__ int wmf_extract_min(const float *key, int m, unsigned used[4]) {
-    int best = -1;
-    float bk = 0.f;
+// Stable ascending order of key[0..m-1] (ties: lower original position first), as a list of positions.
+// Per-thread bottom-up merge sort of 64-bit composites (order-preserving key bits << 32 | position) between two
+// local buffers: O(m log m) instead of the reference's O(m^2) bubble sort, same resulting sequence.
+// (-0.0 is folded onto +0.0 so that it ties with the dummy's 0 exactly as the float comparison does.)
+struct WmfOrder {
+    unsigned long long a[kWmfMax], b[kWmfMax];
+};
+
+__device__ __forceinline__ const unsigned long long *wmf_sort(const float *key, int m, WmfOrder &buf) {
     for (int e = 0; e < m; e++) {
-        if (used[e >> 5] & (1u << (e & 31))) continue;
-        const float k = key[e];
-        if (best < 0 || k < bk) { best = e; bk = k; }
+        const unsigned bits = __float_as_uint(key[e] + 0.0f);
+        const unsigned ord = bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u);
+        buf.a[e] = ((unsigned long long)ord << 32) | (unsigned)e;
     }
-    used[best >> 5] |= 1u << (best & 31);
-    return best;
+    unsigned long long *src = buf.a, *dst = buf.b;
+    for (int width = 1; width < m; width <<= 1) {
+        for (int lo = 0; lo < m; lo += 2 * width) {
+            const int mid = min(lo + width, m), hi = min(lo + 2 * width, m);
+            int i = lo, j = mid;
+            for (int o = lo; o < hi; o++) {
+                const unsigned long long vi = src[min(i, mid - 1)], vj = src[min(j, m - 1)];  // clamped reads; unused when exhausted
+                const bool left = (i < mid) && (j >= hi || vi <= vj);
+                dst[o] = left ? vi : vj;
+                i += left ? 1 : 0;
+                j += left ? 0 : 1;
+            }
+        }
+        unsigned long long *t = src; src = dst; dst = t;
+    }
+    return src;
 }
 
 // first sorted position i < num with cumulative weight >= half; returns the element there or -1
-__device__ __forceinline__ int wmf_weighted_median(const float *key, const float *w, int num, float half) {
-    unsigned used[4] = {0, 0, 0, 0};
+__device__ __forceinline__ int wmf_weighted_median(const float *key, const float *w, int num, float half, WmfOrder &buf) {
+    const unsigned long long *ord = wmf_sort(key, num + 1, buf);
     float acc = 0.f;
     for (int i = 0; i < num; i++) {
-        const int e = wmf_extract_min(key, num + 1, used);
+        const int e = (int)(unsigned)ord[i];
         acc = fadd(acc, w[e]);
         if (acc >= half) return e;
     }
@@ -86,20 +104,23 @@ __device__ __forceinline__ bool wmf_median_plane(const GlueConst &g, const float
                                                  float4 &norm_mid) {
     const int num = L.num;
     // wSum: weights in ascending-depth order, positions 0..num-1 (the largest depth is excluded)
-    unsigned used[4] = {0, 0, 0, 0};
+    WmfOrder buf;
     unsigned char order[kWmfMax];
     float wsum = 0.f;
-    for (int i = 0; i <= num; i++) {
-        const int e = wmf_extract_min(L.d, num + 1, used);
-        order[i] = (unsigned char)e;
-        if (i < num) wsum = fadd(wsum, L.w[e]);
+    {
+        const unsigned long long *ord = wmf_sort(L.d, num + 1, buf);
+        for (int i = 0; i <= num; i++) {
+            const int e = (int)(unsigned)ord[i];
+            order[i] = (unsigned char)e;
+            if (i < num) wsum = fadd(wsum, L.w[e]);
+        }
     }
     const float half = fmul(wsum, 0.5f);
     int e;
     norm_mid = make_float4(0.f, 0.f, 0.f, 0.f);  // (uninitialised in the reference when a median is never reached)
-    if ((e = wmf_weighted_median(L.x, L.w, num, half)) >= 0) norm_mid.x = L.x[e];
-    if ((e = wmf_weighted_median(L.y, L.w, num, half)) >= 0) norm_mid.y = L.y[e];
-    if ((e = wmf_weighted_median(L.z, L.w, num, half)) >= 0) norm_mid.z = L.z[e];
+    if ((e = wmf_weighted_median(L.x, L.w, num, half, buf)) >= 0) norm_mid.x = L.x[e];
+    if ((e = wmf_weighted_median(L.y, L.w, num, half, buf)) >= 0) norm_mid.y = L.y[e];
+    if ((e = wmf_weighted_median(L.z, L.w, num, half, buf)) >= 0) norm_mid.z = L.z[e];
     float acc = 0.f;
     for (int i = 0; i < num; i++) {
         acc = fadd(acc, L.w[order[i]]);
@@ -167,13 +188,215 @@ __global__ void __launch_bounds__(64) wmf_final_kernel(const __grid_constant__ G
     scale_out[p] = sc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// gipuma_WMF, cooperative version.  The per-thread version above keeps ~5 KB of lists per thread in local memory;
+// at any useful occupancy that is far beyond L1 (ncu: local loads 0.4 % L1 hits, 1.6 useful bytes per 32-byte
+// sector, 388 GB of L2 traffic per 2-Mpx level, L2-bound).  Here a CTA of 8 warps owns 8 consecutive pixels:
+//   phase 1 (thread = pixel x neighbour group): the 121 lattice neighbours of the 8 pixels are gathered into shared
+//     memory, pixel-major, together with a per-pixel validity mask (42 KB per CTA -> 5 CTAs = 40 warps per SM);
+//   phase 2 (warp = pixel): the (num+1)-element stable order of each key is a 128-element bitonic sort of
+//     (order-preserving key bits << 32 | neighbour slot) composites held in registers, 4 per lane; the slot number
+//     as low word reproduces the reference's stable order, invalid slots sort to the end, slot 121 is the dummy.
+//     The sorted weight sequences go to a small per-warp scratch and ONE lane per key turns them into running
+//     sums sequentially, so every floating-point sum runs in exactly the reference's order; the medians are then a
+//     warp-wide search for the first running sum >= half.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kCoopPitch = 129;    // slots per pixel (121 neighbours + dummy + padding), odd -> conflict-free columns
+constexpr int kCoopChain = 132;    // pitch of a sorted sequence (the 4 sequences of a warp start on distinct banks)
+constexpr int kCoopSlots = 121, kCoopDummy = 121;
+constexpr int kCoopRun = 8;        // pixels per CTA = warps per CTA
+
+struct WmfCoopSmem {
+    float w[kCoopRun][kCoopPitch], d[kCoopRun][kCoopPitch], x[kCoopRun][kCoopPitch], y[kCoopRun][kCoopPitch], z[kCoopRun][kCoopPitch];
+    unsigned mask[kCoopRun][4];
+    float acc[kCoopRun][4][kCoopChain];          // sorted weights, then their running sums (in place)
+    unsigned char slot[kCoopRun][4][kCoopChain]; // neighbour slot at each sorted position
+};
+
+__device__ __forceinline__ unsigned long long wmf_composite(float key, int slot) {
+    const unsigned bits = __float_as_uint(key + 0.0f);  // -0 -> +0: ties with the dummy's 0 like the float compare
+    const unsigned ord = bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u);
+    return ((unsigned long long)ord << 32) | (unsigned)slot;
+}
+
+// ascending bitonic sort of 128 composites, element e = lane * 4 + r
+__device__ __forceinline__ void wmf_bitonic128(unsigned long long (&v)[4], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 4) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, v[r], j >> 2);
+                    const int e = lane * 4 + r;
+                    const bool up = (e & k) == 0, lower = (e & j) == 0;
+                    const bool take_min = (lower == up);
+                    const unsigned long long mn = v[r] < other ? v[r] : other, mx = v[r] < other ? other : v[r];
+                    v[r] = take_min ? mn : mx;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    if ((r & j) == 0) {
+                        const int e = lane * 4 + r;
+                        const bool up = (e & k) == 0;
+                        const unsigned long long a = v[r], b = v[r ^ j];
+                        const unsigned long long mn = a < b ? a : b, mx = a < b ? b : a;
+                        v[r] = up ? mn : mx;
+                        v[r ^ j] = up ? mx : mn;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 5) wmf_coop_kernel(const __grid_constant__ GlueConst g, const float *__restrict__ ref,
+                                                          const float4 *__restrict__ plane, const float *__restrict__ depth,
+                                                          const float *__restrict__ scale_in, float *__restrict__ scale_out, int iter) {
+    extern __shared__ __align__(16) unsigned char wmf_smem_raw[];
+    WmfCoopSmem &sm = *reinterpret_cast<WmfCoopSmem *>(wmf_smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = g.W, H = g.H;
+    const int y = blockIdx.y, x0 = blockIdx.x * kCoopRun;
+    const int po = 1 << iter, repo = 1 << (3 - iter);
+    const int radius = 80 / po, gap = 16 / po;
+    const float scale_div = (float)repo;
+
+    // ---- phase 1: gather.  thread = (pixel tid & 7, slot group tid >> 3); a warp-wide load covers 4 neighbour
+    // slots x 8 consecutive pixels = four fully used 32-byte sectors.  Slots follow the reference's list order
+    // (x offset outer, y offset inner).
+    if (threadIdx.x < kCoopRun * 4) sm.mask[threadIdx.x >> 2][threadIdx.x & 3] = 0u;
+    if (threadIdx.x < kCoopRun) {  // the dummy element the reference's bubble sort drags in: slot [num] = {0}
+        sm.w[threadIdx.x][kCoopDummy] = 0.f; sm.d[threadIdx.x][kCoopDummy] = 0.f;
+        sm.x[threadIdx.x][kCoopDummy] = 0.f; sm.y[threadIdx.x][kCoopDummy] = 0.f; sm.z[threadIdx.x][kCoopDummy] = 0.f;
+    }
+    __syncthreads();
+    {
+        const int pl = threadIdx.x & (kCoopRun - 1), sg = threadIdx.x >> 3;
+        const int px = x0 + pl;
+        if (px < W) {
+            const float cen = ref[(size_t)y * W + px];
+            for (int c = sg; c < kCoopSlots; c += 32) {
+                const int ii = c / 11, jj = c - ii * 11;
+                const int i = -radius + ii * gap, j = -radius + jj * gap;
+                const int nx = px + i, ny = y + j;
+                if (nx < 0 || nx >= W || ny < 0 || ny >= H) continue;
+                const int ne = ny * W + nx;
+                if (scale_in[ne] != 1.0f) continue;
+                sm.w[pl][c] = wmf_weight(ref[ne], cen, i, j, scale_div);
+                sm.d[pl][c] = depth[ne];
+                const float4 n = plane[ne];
+                sm.x[pl][c] = n.x; sm.y[pl][c] = n.y; sm.z[pl][c] = n.z;
+                atomicOr(&sm.mask[pl][c >> 5], 1u << (c & 31));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: one warp per pixel
+    const int l = warp;
+    const int px = x0 + l;
+    if (px >= W) return;
+    const unsigned m0 = sm.mask[l][0], m1 = sm.mask[l][1], m2 = sm.mask[l][2], m3 = sm.mask[l][3];
+    const int num = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+    const int p = y * W + px;
+    if (num == 0) {
+        if (lane == 0) scale_out[p] = 0.f;
+        return;
+    }
+    // validity of this lane's four slots (slot = lane*4 + r lies in mask word lane/8)
+    const unsigned mw = (lane < 8) ? m0 : (lane < 16) ? m1 : (lane < 24) ? m2 : m3;
+    const unsigned vbits = (mw >> ((lane & 7) * 4)) & 0xFu;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float(*key)[kCoopPitch] = q == 0 ? sm.d : (q == 1 ? sm.x : (q == 2 ? sm.y : sm.z));
+        unsigned long long v[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int slot = lane * 4 + r;
+            if ((vbits >> r) & 1u) v[r] = wmf_composite(key[l][slot], slot);
+            else if (slot == kCoopDummy) v[r] = wmf_composite(0.f, slot);
+            else v[r] = 0xffffffffffffff00ull | (unsigned)slot;
+        }
+        wmf_bitonic128(v, lane);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int s_ = lane * 4 + r;
+            if (s_ < num) {  // positions 0..num-1 are the ones every later loop reads (the largest element is left out)
+                const int slot = (int)(v[r] & 0xffu);
+                sm.acc[l][q][s_] = sm.w[l][slot];
+                sm.slot[l][q][s_] = (unsigned char)slot;
+            }
+        }
+    }
+    __syncwarp();
+    // running sums in sorted order, sequentially (the reference's order of additions): lane q owns sequence q
+    if (lane < 4) {
+        float *seq = sm.acc[l][lane];
+        float acc = 0.f;
+        int s_ = 0;
+        for (; s_ + 4 <= num; s_ += 4) {
+            const float w0 = seq[s_], w1 = seq[s_ + 1], w2 = seq[s_ + 2], w3 = seq[s_ + 3];
+            acc = fadd(acc, w0); seq[s_] = acc;
+            acc = fadd(acc, w1); seq[s_ + 1] = acc;
+            acc = fadd(acc, w2); seq[s_ + 2] = acc;
+            acc = fadd(acc, w3); seq[s_ + 3] = acc;
+        }
+        for (; s_ < num; s_++) { acc = fadd(acc, seq[s_]); seq[s_] = acc; }
+    }
+    __syncwarp();
+    const float half = fmul(sm.acc[l][0][num - 1], 0.5f);  // wSum over the ascending-depth order
+    // weighted medians: first sorted position whose running sum reaches half (0 depth, 1..3 normal components)
+    int hit[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int first = 1 << 20;
+#pragma unroll
+        for (int r = 3; r >= 0; r--) {
+            const int s_ = lane * 4 + r;
+            if (s_ < num && sm.acc[l][q][s_] >= half) first = s_;
+        }
+        first = __reduce_min_sync(0xffffffffu, first);
+        hit[q] = first < num ? (int)sm.slot[l][q][first] : -1;
+    }
+    if (lane == 0) {
+        const int hd = hit[0], hx = hit[1], hy = hit[2], hz = hit[3];
+        float4 norm_mid = make_float4(0.f, 0.f, 0.f, 0.f);  // (uninitialised in the reference when never reached)
+        if (hx >= 0) norm_mid.x = sm.x[l][hx];
+        if (hy >= 0) norm_mid.y = sm.y[l][hy];
+        if (hz >= 0) norm_mid.z = sm.z[l][hz];
+        if (hd >= 0) {
+            const int ii = hd / 11, jj = hd - ii * 11;
+            const int mx = px - radius + ii * gap, my = y - radius + jj * gap;  // weimid
+            const float disp_mid = fdiv(fmul(g.f_params, g.baseline), sm.d[l][hd]);
+            const float len = __fsqrt_rn(dot3(norm_mid.x, norm_mid.x, norm_mid.y, norm_mid.y, norm_mid.z, norm_mid.z));
+            norm_mid.x = fdiv(norm_mid.x, len); norm_mid.y = fdiv(norm_mid.y, len); norm_mid.z = fdiv(norm_mid.z, len);
+            norm_mid.w = g_plane_d(g, norm_mid.x, norm_mid.y, norm_mid.z, mx, my, disp_mid);
+        }
+        const int ths = 24 / po;
+        const float fb = fmul(g.f_params, g.baseline);
+        const float disp_now = fdiv(fb, g_plane_depth(g, norm_mid, px, y));
+        const float disp_org = fdiv(fb, g_plane_depth(g, plane[p], px, y));
+        scale_out[p] = (fabsf(fsub(disp_now, disp_org)) > (float)ths) ? 0.f : 1.f;
+    }
+}
+
 // snapshot = pre-launch copies of the arrays the launch rewrites (scratch supplied by the context)
 static inline int wmf_launch(const GlueConst &g, const float *ref, float4 *plane, float *depth, float *scale, float *scale_snapshot,
-                             int iter, cudaStream_t s) {
+                             int iter, bool per_thread, cudaStream_t s) {
     const size_t n = (size_t)g.W * g.H;
     if (cudaMemcpyAsync(scale_snapshot, scale, n * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return TSAR_ERR_CUDA;
-    dim3 b(32, 2), grid((g.W + 31) / 32, (g.H + 1) / 2);
-    wmf_kernel<<<grid, b, 0, s>>>(g, ref, plane, depth, scale_snapshot, scale, iter);
+    if (per_thread) {  // the first implementation, kept for A/B checks (TSAR_B200_WMF_PER_THREAD=1)
+        dim3 b(32, 2), grid((g.W + 31) / 32, (g.H + 1) / 2);
+        wmf_kernel<<<grid, b, 0, s>>>(g, ref, plane, depth, scale_snapshot, scale, iter);
+    } else {
+        if (cudaFuncSetAttribute(wmf_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WmfCoopSmem)) != cudaSuccess)
+            return TSAR_ERR_CUDA;
+        dim3 grid((g.W + kCoopRun - 1) / kCoopRun, g.H);
+        wmf_coop_kernel<<<grid, 256, sizeof(WmfCoopSmem), s>>>(g, ref, plane, depth, scale_snapshot, scale, iter);
+    }
     return cudaGetLastError() == cudaSuccess ? TSAR_OK : TSAR_ERR_CUDA;
 }
 
