@@ -230,6 +230,33 @@ def test_non_8bit_images_use_fp32_textures(env):
     mine.close(); ref.close()
 
 
+def test_randomized_configurations_bit_exact(env):
+    """Differential sweep against the race-free reference build: random image sizes (odd ones included), view
+    counts, windows, view combinations and depth ranges; the whole per-view sequence must agree bit for bit."""
+    pkg, rb = env
+    L = pkg._lib
+    rng = np.random.RandomState(20240601)
+    for trial in range(8):
+        W, H = int(rng.randint(40, 200)), int(rng.randint(34, 140))
+        V = int(rng.randint(1, 6))
+        box = int(rng.choice([5, 7, 9, 11, 11, 13, 15, 19]))
+        n_best = int(rng.randint(1, min(V, 3) + 1))
+        cost_comb = int(rng.choice([0, 1]))
+        cfg = dict(W=W, H=H, n_images=V + 1, V=V, fx=float(rng.uniform(120, 400)), radius=float(rng.uniform(0.8, 3.0)),
+                   arc_deg=float(rng.uniform(8, 24)))
+        scene = pkg.scene.make_scene(cfg, seed=int(rng.randint(1, 1000)))
+        iters = int(rng.randint(1, 3))
+        params, mine, refs = pc.make_engines(pkg, scene, iterations=iters, box=box, n_best=n_best, cost_comb=cost_comb, variants=("snapshot",))
+        ref = refs["snapshot"]
+        seed = int(rng.randint(1, 2 ** 31))
+        mine.depthmap(seed); ref.depthmap(seed, iters=iters)
+        tag = dict(trial=trial, W=W, H=H, V=V, box=box, n_best=n_best, cost_comb=cost_comb, iters=iters)
+        assert pc.frac_bit_exact(mine.download(L.F_NORM4), ref.download(rb.F_NORM4)) == 1.0, tag
+        assert pc.frac_bit_exact(mine.download(L.F_CONFID), ref.download(rb.F_CONFID)) == 1.0, tag
+        assert (mine.download(L.F_BEVIEW) == ref.download(rb.F_BEVIEW)).all(), tag
+        mine.close(); ref.close()
+
+
 def test_host_entry_matches_resident_path(env, small):
     """tsar_depthmap_host (host buffers in/out, the e2e path) == set_views + depthmap + download."""
     pkg, rb = env
