@@ -62,7 +62,7 @@ typedef struct tsar_params {
     int cost_comb;        /* :75 0 = COMB_ALL, 1 = COMB_BEST_N            */
     float min_disparity;  /* :56 = f*baseline/depthMax (main.cpp:1393)    */
     float max_disparity;  /* :55 = f*baseline/depthMin (main.cpp:1396)    */
-    int color_processing; /* :65 must be 0 (float4 textures are not on the north-star path) */
+    int color_processing; /* :65 accepted; the kernels sample float4 textures with tex2D<float> = channel x, so pass channel x (blue) of each view as its image */
 } tsar_params;
 
 /* gSLICr settings (gSLICr_settings.h:10-21); TSAR's call site: main.cpp:608-615. */

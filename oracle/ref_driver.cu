@@ -56,6 +56,7 @@ struct RefCtx {
     float *c_resize_orig = nullptr;
     size_t guard = 0;
     dim3 grid_cb, block_cb, grid_px, block_px;
+    bool colour = false;  // color_processing: BGRA float4 textures, kernels instantiated for float4 (gipuma.cu:1881-1912)
 };
 
 // wrapper kernel: the reference's pmCostMultiview_cu on explicit (pixel, plane) pairs
@@ -141,7 +142,11 @@ int ref_create(int W, int H, int n_images, const float *const *images, const tsa
     ap.cost_comb = p->cost_comb;
     ap.min_disparity = p->min_disparity;
     ap.max_disparity = p->max_disparity;
-    ap.color_processing = false;
+    ap.color_processing = p->color_processing != 0;
+    r->colour = ap.color_processing;
+#ifndef ORACLE_SNAPSHOT
+    if (r->colour) return -1;  // the float4 instantiations are only built into the snapshot variant
+#endif
     ap.cols = W;
     ap.rows = H;
     ap.depthMin = cams[0].depthMin;
@@ -171,12 +176,22 @@ int ref_create(int W, int H, int n_images, const float *const *images, const tsa
     RCHECK(cudaMallocManaged(&gs.lines->resize4, n * sizeof(float4)));
     memset(gs.lines->resize4, 0, n * sizeof(float4));
 #endif
-    // textures exactly as addImageToTextureFloatGray (main.cpp:1190-1228)
+    // textures exactly as addImageToTextureFloatGray (main.cpp:1190-1228) / addImageToTextureFloatColor (1150-1188);
+    // in colour mode channel x carries the image, the other channels carry different data (they must not matter)
     for (int i = 0; i < n_images; i++) {
-        cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
-        RCHECK(cudaMallocArray(&gs.cuArray[i], &cd, W, H));
-        RCHECK(cudaMemcpy2DToArray(gs.cuArray[i], 0, 0, images[i], (size_t)W * sizeof(float),
-                                   (size_t)W * sizeof(float), H, cudaMemcpyHostToDevice));
+        if (r->colour) {
+            cudaChannelFormatDesc cd = cudaCreateChannelDesc<float4>();
+            RCHECK(cudaMallocArray(&gs.cuArray[i], &cd, W, H));
+            std::vector<float4> px(n);
+            for (size_t k = 0; k < n; k++) px[k] = make_float4(images[i][k], 0.5f * images[i][k] + 3.0f, 255.0f - images[i][k], 0.0f);
+            RCHECK(cudaMemcpy2DToArray(gs.cuArray[i], 0, 0, px.data(), (size_t)W * sizeof(float4), (size_t)W * sizeof(float4), H,
+                                       cudaMemcpyHostToDevice));
+        } else {
+            cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+            RCHECK(cudaMallocArray(&gs.cuArray[i], &cd, W, H));
+            RCHECK(cudaMemcpy2DToArray(gs.cuArray[i], 0, 0, images[i], (size_t)W * sizeof(float),
+                                       (size_t)W * sizeof(float), H, cudaMemcpyHostToDevice));
+        }
         cudaResourceDesc rd;
         memset(&rd, 0, sizeof(rd));
         rd.resType = cudaResourceTypeArray;
@@ -277,10 +292,21 @@ static int set_seed(uint64_t seed) {
     return 0;
 }
 
+// template dispatch on color_processing as gipuma.cu:1881-1912 does
+#ifdef ORACLE_SNAPSHOT
+#define TLAUNCH(K, grid, block, ...)                                        \
+    do {                                                                    \
+        if (r->colour) K<float4><<<grid, block>>>(__VA_ARGS__);             \
+        else K<float><<<grid, block>>>(__VA_ARGS__);                        \
+    } while (0)
+#else
+#define TLAUNCH(K, grid, block, ...) K<float><<<grid, block>>>(__VA_ARGS__)
+#endif
+
 int ref_init(void *h, uint64_t seed) {  // gipuma.cu:1741
     RefCtx *r = (RefCtx *)h;
     if (set_seed(seed)) return -3;
-    gipuma_init_cu2<float><<<r->grid_px, r->block_px>>>(*r->gs);
+    TLAUNCH(gipuma_init_cu2, r->grid_px, r->block_px, *r->gs);
     RCHECK(cudaGetLastError());
     RCHECK(cudaDeviceSynchronize());
     return 0;
@@ -290,24 +316,24 @@ static int launch_kind(RefCtx *r, int kind, uint64_t seed, bool sync) {
     GlobalState &gs = *r->gs;
     switch (kind) {
         case TSAR_BLACK_SPATIAL:
-            gipuma_black_spatialProp_cu<float><<<r->grid_cb, r->block_cb>>>(gs, false);
+            TLAUNCH(gipuma_black_spatialProp_cu, r->grid_cb, r->block_cb, gs, false);
 #ifdef ORACLE_SNAPSHOT
             ref_merge_colour<<<r->grid_px, r->block_px>>>(gs, 0, 32 * (int)r->grid_cb.y);
 #endif
             break;
         case TSAR_BLACK_REFINE:
             if (set_seed(seed)) return -3;
-            gipuma_black_planeRefine_cu<float><<<r->grid_cb, r->block_cb>>>(gs, false);
+            TLAUNCH(gipuma_black_planeRefine_cu, r->grid_cb, r->block_cb, gs, false);
             break;
         case TSAR_RED_SPATIAL:
-            gipuma_red_spatialProp_cu<float><<<r->grid_cb, r->block_cb>>>(gs, false);
+            TLAUNCH(gipuma_red_spatialProp_cu, r->grid_cb, r->block_cb, gs, false);
 #ifdef ORACLE_SNAPSHOT
             ref_merge_colour<<<r->grid_px, r->block_px>>>(gs, 1, 32 * (int)r->grid_cb.y);
 #endif
             break;
         case TSAR_RED_REFINE:
             if (set_seed(seed)) return -3;
-            gipuma_red_planeRefine_cu<float><<<r->grid_cb, r->block_cb>>>(gs, false);
+            TLAUNCH(gipuma_red_planeRefine_cu, r->grid_cb, r->block_cb, gs, false);
             break;
         default:
             return -1;
@@ -339,7 +365,13 @@ int ref_iterate(void *h, int iters, uint64_t seed0) {  // gipuma.cu:1744-1754
         RCHECK(cudaDeviceSynchronize());                     \
         return 0;                                            \
     }
-PX_KERNEL(ref_lrdiff, gipuma_getlrdiff<float>)             // gipuma.cu:1758
+int ref_lrdiff(void *h) {  // gipuma.cu:1758 (samples the textures: typed like the propagation kernels)
+    RefCtx *r = (RefCtx *)h;
+    TLAUNCH(gipuma_getlrdiff, r->grid_px, r->block_px, *r->gs);
+    RCHECK(cudaGetLastError());
+    RCHECK(cudaDeviceSynchronize());
+    return 0;
+}
 PX_KERNEL(ref_getview, gipuma_getview<float>)              // gipuma.cu:1806
 PX_KERNEL(ref_get_disp, gipuma_get_disp<float>)            // gipuma.cu:1755
 PX_KERNEL(ref_update_scale_2, gipuma_update_scale_2<float>)  // gipuma.cu:1875

@@ -29,11 +29,12 @@ def ref_binding():
     return rb
 
 
-def make_engines(pkg, scene, box=11, iterations=8, n_best=1, cost_comb=1, variants=("asis",), device=0):
+def make_engines(pkg, scene, box=11, iterations=8, n_best=1, cost_comb=1, variants=("asis",), device=0, color_processing=0):
     """Returns (params, mine, {variant: RefEngine}) on the same scene."""
     rb = ref_binding()
     params = pkg.make_params(box=box, iterations=iterations, n_best=n_best, cost_comb=cost_comb,
-                             min_disparity=scene["min_disparity"], max_disparity=scene["max_disparity"])
+                             min_disparity=scene["min_disparity"], max_disparity=scene["max_disparity"],
+                             color_processing=color_processing)
     from tsar_mvs_b200.engine import cameras_to_struct
     cams = cameras_to_struct(scene["cams"])
     mine = pkg.DepthmapEngine(device)

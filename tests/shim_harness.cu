@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../include/tsar_b200.h"
 #include "../include/tsar_gipuma_abi.h"
 
@@ -49,9 +51,17 @@ extern "C" int shim_harness_run(int W, int H, int n_images, const float *const *
         c.C4 = make_float4(cams[i].C4[0], cams[i].C4[1], cams[i].C4[2], 0);
         c.fx = cams[i].fx; c.fy = cams[i].fy; c.f = cams[i].f; c.alpha = cams[i].alpha; c.baseline = cams[i].baseline;
         c.depthMin = cams[i].depthMin; c.depthMax = cams[i].depthMax;
-        cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
-        cudaMallocArray(&gs->cuArray[i], &cd, W, H);
-        cudaMemcpy2DToArray(gs->cuArray[i], 0, 0, images[i], (size_t)W * 4, (size_t)W * 4, H, cudaMemcpyHostToDevice);
+        if (p->color_processing) {  // addImageToTextureFloatColor (main.cpp:1150-1188): BGRA float4, the image in channel x
+            cudaChannelFormatDesc cd = cudaCreateChannelDesc<float4>();
+            cudaMallocArray(&gs->cuArray[i], &cd, W, H);
+            std::vector<float4> px(n);
+            for (size_t k = 0; k < n; k++) px[k] = make_float4(images[i][k], 7.0f, 255.0f - images[i][k], 0.0f);
+            cudaMemcpy2DToArray(gs->cuArray[i], 0, 0, px.data(), (size_t)W * 16, (size_t)W * 16, H, cudaMemcpyHostToDevice);
+        } else {
+            cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+            cudaMallocArray(&gs->cuArray[i], &cd, W, H);
+            cudaMemcpy2DToArray(gs->cuArray[i], 0, 0, images[i], (size_t)W * 4, (size_t)W * 4, H, cudaMemcpyHostToDevice);
+        }
         cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
         rd.resType = cudaResourceTypeArray; rd.res.array.array = gs->cuArray[i];
         cudaTextureDesc td; memset(&td, 0, sizeof(td));
@@ -62,7 +72,7 @@ extern "C" int shim_harness_run(int W, int H, int n_images, const float *const *
     AlgorithmParameters &ap = *gs->params;
     ap.box_hsize = p->box_hsize; ap.box_vsize = p->box_vsize; ap.iterations = p->iterations; ap.n_best = p->n_best;
     ap.cost_comb = p->cost_comb; ap.min_disparity = p->min_disparity; ap.max_disparity = p->max_disparity;
-    ap.color_processing = false; ap.cols = W; ap.rows = H;
+    ap.color_processing = p->color_processing != 0; ap.cols = W; ap.rows = H;
     LineState &l = *gs->lines;  // LineState::resize (linestate.h:73-109)
     l.c = managed<float>(n); l.depth = managed<float>(n); l.fakedepth = managed<float>(n); l.norm4 = managed<float4>(n);
     l.scale = managed<float>(n); l.ransa = managed<float>(n); l.canny = managed<float>(n); l.ratio = managed<float>(n);

@@ -257,6 +257,26 @@ def test_randomized_configurations_bit_exact(env):
         mine.close(); ref.close()
 
 
+def test_color_processing_is_the_grey_path_on_channel_x(env):
+    """`-color_processing`: the reference uploads BGRA float4 textures and instantiates its kernels for float4, but they
+    still sample with tex2D<float> (gipuma.cu:247,262,265), i.e. the first component.  The reference build run that way
+    (channel x = the image, other channels different data) must equal our path fed with channel x."""
+    pkg, rb = env
+    L = pkg._lib
+    scene = pkg.scene.make_scene("tiny")
+    params, mine, refs = pc.make_engines(pkg, scene, iterations=2, variants=("snapshot",), color_processing=1)
+    ref = refs["snapshot"]
+    mine.depthmap(SEED); ref.depthmap(SEED, iters=2)
+    assert pc.frac_bit_exact(mine.download(L.F_NORM4), ref.download(rb.F_NORM4)) == 1.0
+    assert pc.frac_bit_exact(mine.download(L.F_CONFID), ref.download(rb.F_CONFID)) == 1.0
+    # and it is the same result as the grey build on that image
+    params, grey, _ = pc.make_engines(pkg, scene, iterations=2, variants=())
+    grey.depthmap(SEED)
+    assert pc.frac_bit_exact(mine.download(L.F_NORM4), grey.download(L.F_NORM4)) == 1.0
+    for e in (mine, ref, grey):
+        e.close()
+
+
 def test_host_entry_matches_resident_path(env, small):
     """tsar_depthmap_host (host buffers in/out, the e2e path) == set_views + depthmap + download."""
     pkg, rb = env
@@ -353,6 +373,17 @@ def test_reference_entry_points_drop_in(env, small):
     cf = eng.download(L.F_CONFID)
     eng.update_scale_2(); eng.update_scale(); eng.compute_disp()
     assert pc.frac_bit_exact(s_cf, cf) == 1.0
+    # the same through BGRA float4 arrays (color_processing): the shim takes channel x, as the kernels would
+    params_grey = params
+    params = pkg.make_params(box=11, iterations=2, min_disparity=scene["min_disparity"], max_disparity=scene["max_disparity"],
+                             color_processing=1)
+    os.environ["TSAR_B200_PATCHMATCH"] = "1"
+    try:
+        c_n4, c_cf, _, _ = run(False)
+    finally:
+        del os.environ["TSAR_B200_PATCHMATCH"]
+    params = params_grey
+    assert pc.frac_bit_exact(c_n4, s_n4) == 1.0 and pc.frac_bit_exact(c_cf, s_cf) == 1.0
     assert pc.frac_bit_exact(s_n4, eng.download(L.F_NORM4)) == 1.0
     assert pc.frac_bit_exact(s_fd, eng.download(L.F_FAKEDEPTH)) == 1.0
     assert pc.frac_bit_exact(s_sc, eng.download(L.F_SCALE)) == 1.0

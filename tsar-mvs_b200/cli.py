@@ -122,14 +122,16 @@ def write_pair_txt(path, neighbours):
             f.write(f"{i}\n{len(nb)} " + " ".join(f"{k} 1.0" for k in nb) + "\n")
 
 
-def _imread_gray(path):
+def _imread_gray(path, colour=False):
+    """Grey image (cv::imread IMREAD_GRAYSCALE, main.cpp:1302).  With -color_processing the reference uploads the
+    BGRA image instead and its kernels sample the first component (tex2D<float>, gipuma.cu:247,262,265): blue."""
     if path.endswith(".npy"):
         return np.load(path).astype(np.float32)
-    import cv2  # image decoding only (the reference uses cv::imread, main.cpp:1302)
-    im = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+    import cv2  # image decoding only
+    im = cv2.imread(path, cv2.IMREAD_COLOR if colour else cv2.IMREAD_GRAYSCALE)
     if im is None:
         raise FileNotFoundError(path)
-    return im.astype(np.float32)
+    return (im[..., 0] if colour else im).astype(np.float32)
 
 
 def write_synthetic_dataset(cfg_name, root):
@@ -168,7 +170,7 @@ def run(argv):
     names = opt["images"]
     stem = names[0][:8]                         # main.cpp:1462: numind = imgname.substr(0, 8)
     camera_id = int(names[0][4:8])              # main.cpp:1347-1349: atoi(name.substr(4, 8)) (sic: 4 characters)
-    images = [_imread_gray(os.path.join(opt["images_folder"], n)) for n in names]
+    images = [_imread_gray(os.path.join(opt["images_folder"], n), opt["color_processing"]) for n in names]
     Ks, Rs, ts, dmin, dmax = [], [], [], None, None
     for i, n in enumerate(names):
         K, R, t, a, b = read_cam_txt(os.path.join(mslp, "cams", f"{n[:8]}_cam.txt"))
@@ -268,7 +270,7 @@ def run_all_views(opt, mslp):
     by_id = {c: k for k, c in enumerate(ids)}
     krt = [read_cam_txt(os.path.join(mslp, "cams", f"{n[:8]}_cam.txt")) for n in names]
     t0 = time.perf_counter()
-    pool = [torch.from_numpy(_imread_gray(os.path.join(folder, n))).to(f"cuda:{dev}") for n in names]   # resident, once
+    pool = [torch.from_numpy(_imread_gray(os.path.join(folder, n), opt["color_processing"])).to(f"cuda:{dev}") for n in names]   # resident, once
     H, W = pool[0].shape
     mine = views_for_rank(len(names), rank, world)
     lanes = []

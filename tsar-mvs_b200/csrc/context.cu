@@ -504,7 +504,9 @@ int tsar_set_views(tsar_ctx *ctx, int W, int H, int n_images, const float *const
 int tsar_set_params(tsar_ctx *ctx, const tsar_params *p) {
     if (!ctx || !p) return TSAR_ERR_ARG;
     if (p->box_hsize < 1 || p->box_vsize < 1 || p->n_best < 1) FAIL(TSAR_ERR_ARG, "bad window / n_best");
-    if (p->color_processing) FAIL(TSAR_ERR_ARG, "color_processing (float4 textures) is outside the north-star path");
+    // color_processing: the reference then uploads BGRA float4 textures, but every kernel still samples them with
+    // tex2D<float> (gipuma.cu:247, 262, 265, 341, 356, 359), which returns the first component: the arithmetic is
+    // the grey path on channel x (blue).  Callers pass that channel as the view image; nothing else changes.
     ctx->params = *p;
     ctx->have_params = true;
     return rebuild_constants(ctx);

@@ -20,6 +20,11 @@ namespace {
 
 typedef tsar_abi::GlobalState AbiState;
 
+__global__ void first_channel_kernel(const float4 *__restrict__ in, float *__restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i].x;
+}
+
 struct ShimCtx {
     tsar_ctx *ctx = nullptr;
     bool views = false;
@@ -60,15 +65,31 @@ int ensure_views(AbiState &gs, ShimCtx &s) {
         o.fx = c.fx; o.fy = c.fy; o.f = c.f; o.alpha = c.alpha; o.baseline = c.baseline;
         o.depthMin = c.depthMin; o.depthMax = c.depthMax;
     }
-    // the caller uploaded the images into cudaArrays (addImageToTextureFloatGray, main.cpp:1190-1228)
+    // the caller uploaded the images into cudaArrays: float (addImageToTextureFloatGray, main.cpp:1190-1228) or, with
+    // color_processing, BGRA float4 (addImageToTextureFloatColor, main.cpp:1150-1188) of which the kernels only ever
+    // sample the first component (tex2D<float>, gipuma.cu:247,262,265)
+    const bool colour = gs.params->color_processing;
     std::vector<float *> dev_imgs(n_images, nullptr);
+    float4 *rgba = nullptr;
+    if (colour && cudaMalloc(&rgba, (size_t)W * H * 16) != cudaSuccess) return TSAR_ERR_CUDA;
     for (int i = 0; i < n_images; i++) {
-        if (cudaMalloc(&dev_imgs[i], (size_t)W * H * 4) != cudaSuccess ||
-            cudaMemcpy2DFromArray(dev_imgs[i], (size_t)W * 4, gs.cuArray[i], 0, 0, (size_t)W * 4, H, cudaMemcpyDeviceToDevice) != cudaSuccess) {
+        bool ok = cudaMalloc(&dev_imgs[i], (size_t)W * H * 4) == cudaSuccess;
+        if (ok && !colour)
+            ok = cudaMemcpy2DFromArray(dev_imgs[i], (size_t)W * 4, gs.cuArray[i], 0, 0, (size_t)W * 4, H, cudaMemcpyDeviceToDevice) == cudaSuccess;
+        if (ok && colour) {
+            ok = cudaMemcpy2DFromArray(rgba, (size_t)W * 16, gs.cuArray[i], 0, 0, (size_t)W * 16, H, cudaMemcpyDeviceToDevice) == cudaSuccess;
+            if (ok) {
+                first_channel_kernel<<<(unsigned)(((size_t)W * H + 255) / 256), 256>>>(rgba, dev_imgs[i], (size_t)W * H);
+                ok = cudaDeviceSynchronize() == cudaSuccess;
+            }
+        }
+        if (!ok) {
             fprintf(stderr, "[tsar_b200 shim] reading view %d from its cudaArray failed: %s\n", i, cudaGetErrorString(cudaGetLastError()));
+            cudaFree(rgba);
             return TSAR_ERR_CUDA;
         }
     }
+    cudaFree(rgba);
     std::vector<int> subset(cp.viewSelectionSubset, cp.viewSelectionSubset + V);
     int rc = tsar_set_views(s.ctx, W, H, n_images, dev_imgs.data(), 1, cams.data(), cp.f, subset.data(), V);
     for (float *p : dev_imgs) cudaFree(p);

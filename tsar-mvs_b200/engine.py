@@ -23,9 +23,9 @@ class TsarError(RuntimeError):
     pass
 
 
-def make_params(box=11, iterations=8, n_best=1, cost_comb=1, min_disparity=0.0, max_disparity=256.0):
+def make_params(box=11, iterations=8, n_best=1, cost_comb=1, min_disparity=0.0, max_disparity=256.0, color_processing=0):
     """AlgorithmParameters as the run scripts set them (scripts/pipes.sh:10-15)."""
-    return L.TsarParams(box, box, iterations, n_best, cost_comb, min_disparity, max_disparity, 0)
+    return L.TsarParams(box, box, iterations, n_best, cost_comb, min_disparity, max_disparity, int(color_processing))
 
 
 def cameras_to_struct(cams):
