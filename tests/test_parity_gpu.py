@@ -277,6 +277,30 @@ def test_color_processing_is_the_grey_path_on_channel_x(env):
         e.close()
 
 
+def test_context_reuse_across_sizes_and_view_counts(env):
+    """One context processes views of different sizes / view counts / windows one after the other (what a multi-view
+    driver does); every result equals a fresh context's."""
+    pkg, rb = env
+    L = pkg._lib
+    from tsar_mvs_b200.engine import cameras_to_struct
+    cases = [("tiny", 11, 2), (dict(W=150, H=90, n_images=6, V=5, fx=260.0, radius=1.5, arc_deg=18.0), 19, 1),
+             (dict(W=67, H=33, n_images=3, V=2, fx=150.0, radius=1.0, arc_deg=14.0), 7, 2), ("tiny", 11, 2)]
+    shared = pkg.DepthmapEngine(0)
+    for cfg, box, iters in cases:
+        scene = pkg.scene.make_scene(cfg)
+        params = pkg.make_params(box=box, iterations=iters, min_disparity=scene["min_disparity"], max_disparity=scene["max_disparity"])
+        outs = []
+        for eng in (shared, pkg.DepthmapEngine(0)):
+            eng.set_views(scene["images"], cameras_to_struct(scene["cams"]), scene["subset"], cam_f=scene["cam_f"])
+            eng.set_params(params)
+            eng.depthmap(SEED)
+            outs.append((eng.download(L.F_NORM4), eng.download(L.F_CONFID)))
+            if eng is not shared:
+                eng.close()
+        assert pc.frac_bit_exact(outs[0][0], outs[1][0]) == 1.0 and pc.frac_bit_exact(outs[0][1], outs[1][1]) == 1.0, cfg
+    shared.close()
+
+
 def test_host_entry_matches_resident_path(env, small):
     """tsar_depthmap_host (host buffers in/out, the e2e path) == set_views + depthmap + download."""
     pkg, rb = env
