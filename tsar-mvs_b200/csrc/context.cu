@@ -64,6 +64,8 @@ struct tsar_ctx {
     int n_regions = 0;
     uint32_t *rng = nullptr;
     size_t rng_alloc = 0;
+    uint32_t *rng_batch = nullptr;             // tables of all refinement launches of one tsar_iterate call
+    size_t rng_batch_alloc = 0;
     int rng_pitch = 0, rng_len = 0;
     // scratch for tsar_eval_planes
     void *scratch = nullptr;
@@ -271,7 +273,7 @@ static int make_rng_table(tsar_ctx *ctx, uint64_t seed) {
     return TSAR_OK;
 }
 
-static int launch_checker(tsar_ctx *ctx, int mode, int colour) {
+static int launch_checker(tsar_ctx *ctx, int mode, int colour, const uint32_t *rng_table = nullptr) {
     CheckerArgs a;
     for (int col = 0; col < 2; col++) { a.plane_in[col] = ctx->plane[ctx->cur[col]]; a.cost_in[col] = ctx->cost[ctx->cur[col]]; }
     const bool sp = (mode & PM_MODE_SP) != 0;
@@ -280,7 +282,7 @@ static int launch_checker(tsar_ctx *ctx, int mode, int colour) {
     a.cost_out = ctx->cost[out];
     a.ratio = ctx->ratio;
     a.beview = ctx->beview;
-    a.rng = ctx->rng;
+    a.rng = rng_table ? rng_table : ctx->rng;
     a.colour = colour;
     cudaEvent_t p0 = nullptr, p1 = nullptr;
     if (ctx->profiling) {
@@ -353,7 +355,7 @@ int tsar_destroy(tsar_ctx *ctx) {
     free_state(ctx);
     free_images(ctx);
     for (auto &pr : ctx->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-    cudaFree(ctx->d_tex); cudaFree(ctx->d_cams); cudaFree(ctx->rng); cudaFree(ctx->scratch);
+    cudaFree(ctx->d_tex); cudaFree(ctx->d_cams); cudaFree(ctx->rng); cudaFree(ctx->rng_batch); cudaFree(ctx->scratch);
     cudaFree(ctx->region_text); cudaFree(ctx->region_plane); cudaFree(ctx->d_flag); cudaFree(ctx->stage32);
     slic_free(ctx->slic);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -562,18 +564,35 @@ int tsar_iterate(tsar_ctx *ctx, int iters, uint64_t seed0, const uint64_t *refin
     int rc = need_ready(ctx);
     if (rc) return rc;
     if (!ctx->have_planes) FAIL(TSAR_ERR_STATE, "no planes: call tsar_init_planes or tsar_load_planes first");
+    // XORWOW row tables of ALL refinement launches of this loop in one launch (a single table occupies 5 % of the
+    // GPU): 2*iters tables of H x pitch words, when that fits a 4 GB budget and the batch limit
+    const size_t table_words = (size_t)ctx->rng_pitch * ctx->H;
+    const int n_tables = 2 * iters;
+    const bool batch = iters > 0 && n_tables <= kRngBatchMax && table_words * n_tables * 4 <= ((size_t)4 << 30);
+    if (batch) {
+        if (table_words * n_tables > ctx->rng_batch_alloc) {
+            cudaFree(ctx->rng_batch); ctx->rng_batch = nullptr; ctx->rng_batch_alloc = 0;
+            CK(cudaMalloc(&ctx->rng_batch, table_words * n_tables * 4));
+            ctx->rng_batch_alloc = table_words * n_tables;
+        }
+        unsigned long long seeds[kRngBatchMax];
+        for (int t = 0; t < n_tables; t++) seeds[t] = refine_seeds ? refine_seeds[t] : seed0 + 1 + (uint64_t)t;
+        CK(pm_launch_rng_tables(ctx->rng_batch, table_words, n_tables, seeds, ctx->rng_pitch, ctx->H, ctx->rng_len, ctx->stream));
+        ctx->launches++;
+    }
     for (int it = 0; it < iters; it++) {
         for (int col = 0; col < 2; col++) {
             const uint64_t seed = refine_seeds ? refine_seeds[2 * it + col] : seed0 + 1 + 2 * (uint64_t)it + col;
+            const uint32_t *table = batch ? ctx->rng_batch + table_words * (2 * it + col) : nullptr;
             if (ctx->fused) {
                 // spatial propagation and refinement of one colour in ONE kernel: the refinement of a
                 // pixel depends only on that pixel's own state after propagation
-                if ((rc = make_rng_table(ctx, seed))) return rc;
-                if ((rc = launch_checker(ctx, PM_MODE_FUSED, col))) return rc;
+                if (!batch && (rc = make_rng_table(ctx, seed))) return rc;
+                if ((rc = launch_checker(ctx, PM_MODE_FUSED, col, table))) return rc;
             } else {
                 if ((rc = launch_checker(ctx, PM_MODE_SP, col))) return rc;
-                if ((rc = make_rng_table(ctx, seed))) return rc;
-                if ((rc = launch_checker(ctx, PM_MODE_PR, col))) return rc;
+                if (!batch && (rc = make_rng_table(ctx, seed))) return rc;
+                if ((rc = launch_checker(ctx, PM_MODE_PR, col, table))) return rc;
             }
         }
     }

@@ -37,6 +37,10 @@ extern const PmVariant pm_variant_w19;      // 19x19 window (hRad 9, 100 samples
 extern const PmVariant pm_variant_generic;  // any window, any combination (run-time loops)
 
 cudaError_t pm_launch_rng_table(uint32_t *table, int pitch, int H, int len, unsigned long long seed, cudaStream_t);
+// n_tables (<= kRngBatchMax) tables in one launch, table t at tables + t * stride, seeded seeds[t]
+constexpr int kRngBatchMax = 64;
+cudaError_t pm_launch_rng_tables(uint32_t *tables, size_t stride, int n_tables, const unsigned long long *seeds, int pitch, int H,
+                                 int len, cudaStream_t);
 cudaError_t pm_launch_merge_colour(int W, int H, int colour, const float4 *psrc, const float *csrc, float4 *pdst,
                                    float *cdst, cudaStream_t);
 

@@ -102,53 +102,52 @@ __global__ void slic_assign_kernel(const float4 *__restrict__ lab, const SpixelI
     if (minidx >= 0) idx[y * w + x] = minidx;
 }
 
-// Update_Cluster_Center_device + Finalize_Reduction_Result_device (GPU.cu:260-369, shared.h:153-175), parity mode
+// Update_Cluster_Center_device + Finalize_Reduction_Result_device (GPU.cu:260-369, shared.h:153-175), parity mode.
+// Of the 256 slots of a 16x16 sub-block only 28 reach thread 0's result in the compiled reference:
+// slots k, k+128, k+64, k+192 for k in {0, 32, 16, 8, 4, 2, 1}, summed as ((o_k + o_k+128) + (o_k+64 + o_k+192)) and then
+// chained in that order of k.  One warp per superpixel: lane 4*q + part loads slot (k_q, part); two xor-shuffles
+// form the four-slot sums with exactly that association (float addition is commutative), lane 0 chains the seven of
+// them and accumulates over the sub-blocks in order.
 __global__ void slic_update_parity_kernel(const float4 *__restrict__ lab, const int *__restrict__ idx,
                                           SpixelInfo *__restrict__ sp, int mw, int mh, int w, int h, int size,
                                           int nblocks, int nbpl) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= mw * mh) return;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s >= mw * mh) return;  // whole warps
     const int sx = s % mw, sy = s / mw;
     const int x_start = sx * size - size, y_start = sy * size - size;
+    const int q = lane >> 2, part = lane & 3;
+    const int kq = q == 0 ? 0 : (64 >> q);                          // 0, 32, 16, 8, 4, 2, 1 (q = 7: unused lanes)
+    const int off = part == 0 ? 0 : (part == 1 ? 128 : (part == 2 ? 64 : 192));
+    const int id = kq + off;
     float ccx = 0.f, ccy = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
     int count = 0;
     for (int z = 0; z < nblocks; z++) {
         const int bx = z % nbpl, by = z / nbpl;
-        float S[7][5];
-        int cnt = 0;
-        const int slots[7] = {0, 32, 16, 8, 4, 2, 1};
-#pragma unroll
-        for (int q = 0; q < 7; q++) {
-            float o[4][5];
-#pragma unroll
-            for (int part = 0; part < 4; part++) {  // k, k+128, k+64, k+192
-                const int offs[4] = {0, 128, 64, 192};
-                const int id = slots[q] + offs[part];
-                const int xo = bx * 16 + (id & 15), yo = by * 16 + (id >> 4);
-                o[part][0] = o[part][1] = o[part][2] = o[part][3] = o[part][4] = 0.f;
-                if (xo < size * 3 && yo < size * 3) {
-                    const int xi = x_start + xo, yi = y_start + yo;
-                    if (xi >= 0 && xi < w && yi >= 0 && yi < h && idx[yi * w + xi] == s) {
-                        const float4 c = lab[yi * w + xi];
-                        o[part][0] = c.x; o[part][1] = c.y; o[part][2] = c.z; o[part][3] = (float)xi; o[part][4] = (float)yi;
-                        cnt++;
-                    }
-                }
+        float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        int hit = 0;
+        const int xo = bx * 16 + (id & 15), yo = by * 16 + (id >> 4);
+        if (q < 7 && xo < size * 3 && yo < size * 3) {
+            const int xi = x_start + xo, yi = y_start + yo;
+            if (xi >= 0 && xi < w && yi >= 0 && yi < h && idx[yi * w + xi] == s) {
+                const float4 c = lab[yi * w + xi];
+                o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = (float)xi; o[4] = (float)yi;
+                hit = 1;
             }
-#pragma unroll
-            for (int e = 0; e < 5; e++) S[q][e] = fadd(fadd(o[0][e], o[1][e]), fadd(o[2][e], o[3][e]));
         }
-        float part5[5];
+        count += __popc(__ballot_sync(0xffffffffu, hit));
 #pragma unroll
         for (int e = 0; e < 5; e++) {
-            float a = fadd(S[0][e], S[1][e]);
-            a = fadd(a, S[2][e]); a = fadd(a, S[3][e]); a = fadd(a, S[4][e]); a = fadd(a, S[5][e]); a = fadd(a, S[6][e]);
-            part5[e] = a;
+            float v = fadd(o[e], __shfl_xor_sync(0xffffffffu, o[e], 1));   // (o_k + o_k+128) | (o_k+64 + o_k+192)
+            v = fadd(v, __shfl_xor_sync(0xffffffffu, v, 2));               // S[q] on every lane of the group
+            float a = v;                                                   // lane 0: S[0]
+#pragma unroll
+            for (int g = 1; g < 7; g++) a = fadd(a, __shfl_sync(0xffffffffu, v, 4 * g));
+            o[e] = a;                                                      // meaningful on lane 0
         }
-        c0 = fadd(c0, part5[0]); c1 = fadd(c1, part5[1]); c2 = fadd(c2, part5[2]);
-        ccx = fadd(ccx, part5[3]); ccy = fadd(ccy, part5[4]);
-        count += cnt;
+        c0 = fadd(c0, o[0]); c1 = fadd(c1, o[1]); c2 = fadd(c2, o[2]);
+        ccx = fadd(ccx, o[3]); ccy = fadd(ccy, o[4]);
     }
+    if (lane != 0) return;
     SpixelInfo out = sp[s];
     out.no_pixels = count;
     if (count != 0) {
@@ -237,7 +236,7 @@ static inline const char *slic_run(SlicState &st, const unsigned char *bgrx, con
         if (cfg.correct_reduction)
             slic_update_full_kernel<<<(nsp * 32 + 127) / 128, 128, 0, stream>>>(st.d_lab, st.d_idx, st.d_sp, mw, mh, w, h, size);
         else
-            slic_update_parity_kernel<<<(nsp + 63) / 64, 64, 0, stream>>>(st.d_lab, st.d_idx, st.d_sp, mw, mh, w, h, size, nblocks, nbpl);
+            slic_update_parity_kernel<<<(nsp * 32 + 127) / 128, 128, 0, stream>>>(st.d_lab, st.d_idx, st.d_sp, mw, mh, w, h, size, nblocks, nbpl);
         slic_assign_kernel<<<gp, b, 0, stream>>>(st.d_lab, st.d_sp, st.d_idx, mw, mh, w, h, size, cfg.coh_weight, norm_xy);
         *n_launches += 2;
     }
