@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""Times the launch-shape variants of the 11x11 PatchMatch kernels on a bench-sized scene and checks that
+"""(The launch-shape variants c g h i e f need the experimental pm_inst_w11<x>.cu translation units of the commit that
+introduced this note; the default build only has the u8/f32 texel variants.)
+Times the launch-shape variants of the 11x11 PatchMatch kernels on a bench-sized scene and checks that
 they all give identical output (development tooling)."""
 import json
 import os
@@ -12,7 +14,7 @@ import torch
 from tests import parity_common as pc
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
-variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ["u8", "f32"]
+variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ["u8", "f32"]   # u8 | f32 | w11 launch shapes: c g h i e f
 pkg = pc.load_pkg()
 L = pkg._lib
 scene = pkg.scene.make_scene(cfg, backend="torch", device="cuda:0")
@@ -23,6 +25,7 @@ params = pkg.make_params(box=11, iterations=8, min_disparity=scene["min_disparit
 res, base = {}, None
 for v in variants:
     os.environ["TSAR_B200_NO_U8"] = "1" if v == "f32" else "0"
+    os.environ["TSAR_B200_W11_VARIANT"] = v if v in ("c", "g", "h", "i", "e", "f", "q") else ""
     eng = pkg.DepthmapEngine(0)
     eng.set_views_device([t.data_ptr() for t in imgs], scene["W"], scene["H"], cams, scene["subset"], cam_f=scene["cam_f"])
     eng.set_params(params)

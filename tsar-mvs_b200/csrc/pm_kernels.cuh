@@ -6,7 +6,18 @@
 #include "pm_core.cuh"
 #include "pm_launch.h"
 
+// Kernels are templates; two translation units that instantiate the same template arguments with different macro
+// settings (PM_FAST_UNROLL, PM_WARP_COLS) would otherwise share one symbol and silently run the same code.  Each
+// variant TU therefore places its kernels in its own namespace.
+#ifndef PM_KERNEL_NS
+#define PM_KERNEL_NS pm_default
+#endif
+#ifndef PM_WARP_COLS
+#define PM_WARP_COLS 32   // columns of the CTA tile covered by one warp: 32 (1 row pair), 16 (2 row pairs) or 8 (4)
+#endif
+
 namespace tsar {
+namespace PM_KERNEL_NS {
 
 // shared memory carve-up common to the window kernels
 template <int NT>
@@ -108,9 +119,19 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
     fill_spatial_table<N1>(c, sm.sp, tid, NT);
     __syncthreads();
     // block = 32 columns x (NT/32) row pairs; lane parity selects the row of the pair exactly as the reference's
-    // wrappers do (gipuma.cu:1099-1103).  (More compact warp footprints were measured: no difference.)
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = (blockIdx.y * (NT / 32) + threadIdx.y) * 2 + ((x + a.colour) & 1);
+    // wrappers do (gipuma.cu:1099-1103).  (More compact warp footprints, PM_WARP_COLS = 16 or 8, measure the same to 0.3 %: texture wavefronts are per quad.)
+#if defined(PM_QUAD_VERTICAL)
+    // experiment: the four lanes of a texture quad take a 2-column x 4-row zigzag instead of 4 columns x 2 rows
+    // (warp = 16 columns x 4 rows); needs NT = 128
+    const int lane_ = threadIdx.x, w_ = threadIdx.y;
+    const int y = (int)blockIdx.y * 8 + (w_ >> 1) * 4 + (lane_ & 3);
+    const int x = (int)blockIdx.x * 32 + (w_ & 1) * 16 + 2 * (lane_ >> 2) + ((a.colour + y) & 1);
+#else
+    constexpr int WC = PM_WARP_COLS, WPR = 32 / WC;   // warps side by side in the 32-column tile
+    const int x = blockIdx.x * 32 + ((int)threadIdx.y % WPR) * WC + ((int)threadIdx.x % WC);
+    const int rowpair = ((int)threadIdx.y / WPR) * (32 / WC) + ((int)threadIdx.x / WC);
+    const int y = (blockIdx.y * (NT / 32) + rowpair) * 2 + ((x + a.colour) & 1);
+#endif
     if (x >= W || y >= H || y >= c.y_limit) return;
     const int own = a.colour;
     const int pidx = y * W + x;
@@ -119,7 +140,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
     WS wt;
     if constexpr (TILE) {
         wt.w = reinterpret_cast<float *>(smem_raw) + tid;
-        wt.rt = tile + (y - (int)blockIdx.y * (NT / 32) * 2) * kTilePitch + threadIdx.x;
+        wt.rt = tile + (y - (int)blockIdx.y * (NT / 32) * 2) * kTilePitch + (x - (int)blockIdx.x * 32);
     } else {
         wt.p = sm.wt + tid;
     }
@@ -325,4 +346,6 @@ __global__ void __launch_bounds__(NT, MINB) pm_cost_of_state_kernel(const __grid
     cost[p] = multiview_cost<NT, N1, GEN, false, U8>(c, x, y, plane[p], wt, rs).cost;
 }
 
+}  // namespace PM_KERNEL_NS
+using namespace PM_KERNEL_NS;
 }  // namespace tsar
