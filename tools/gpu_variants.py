@@ -25,7 +25,7 @@ params = pkg.make_params(box=11, iterations=8, min_disparity=scene["min_disparit
 res, base = {}, None
 for v in variants:
     os.environ["TSAR_B200_NO_U8"] = "1" if v == "f32" else "0"
-    os.environ["TSAR_B200_W11_VARIANT"] = v if v in ("c", "g", "h", "i", "e", "f", "q") else ""
+    os.environ["TSAR_B200_W11_VARIANT"] = v if v in ("c", "g", "h", "i", "e", "f", "q", "r") else ""
     eng = pkg.DepthmapEngine(0)
     eng.set_views_device([t.data_ptr() for t in imgs], scene["W"], scene["H"], cams, scene["subset"], cam_f=scene["cam_f"])
     eng.set_params(params)

@@ -3,7 +3,8 @@
 // (36 texture fetches in flight per thread).  Chosen by measurement on B200 (profiles/r01_variants_C2.json, checker
 // kernel ms at C2): this shape 19.51; >= 5 CTAs/SM (96 regs) 20.1-20.6; >= 6 (80 regs) 21.3; >= 3 (168 regs) 22.1;
 // warps covering 16 x 2 or 8 x 4 row pairs (PM_WARP_COLS) 19.56 / 19.58; texture quads of 2 columns x 4 rows instead
-// of 4 x 2 (PM_QUAD_VERTICAL) 20.18.  All shapes give bit-identical output.
+// of 4 x 2: 20.18; one image row per warp (quad = 7 x 1 pixels): 19.67.  All shapes give bit-identical output
+// (the quad / row mappings were experiments of the commit that recorded them and are not kept in the kernel).
 #define PM_FAST_UNROLL(n1) (n1)
 #define PM_VARIANT pm_variant_w11
 #define PM_LABEL "w11"

@@ -120,18 +120,10 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
     __syncthreads();
     // block = 32 columns x (NT/32) row pairs; lane parity selects the row of the pair exactly as the reference's
     // wrappers do (gipuma.cu:1099-1103).  (More compact warp footprints, PM_WARP_COLS = 16 or 8, measure the same to 0.3 %: texture wavefronts are per quad.)
-#if defined(PM_QUAD_VERTICAL)
-    // experiment: the four lanes of a texture quad take a 2-column x 4-row zigzag instead of 4 columns x 2 rows
-    // (warp = 16 columns x 4 rows); needs NT = 128
-    const int lane_ = threadIdx.x, w_ = threadIdx.y;
-    const int y = (int)blockIdx.y * 8 + (w_ >> 1) * 4 + (lane_ & 3);
-    const int x = (int)blockIdx.x * 32 + (w_ & 1) * 16 + 2 * (lane_ >> 2) + ((a.colour + y) & 1);
-#else
     constexpr int WC = PM_WARP_COLS, WPR = 32 / WC;   // warps side by side in the 32-column tile
     const int x = blockIdx.x * 32 + ((int)threadIdx.y % WPR) * WC + ((int)threadIdx.x % WC);
     const int rowpair = ((int)threadIdx.y / WPR) * (32 / WC) + ((int)threadIdx.x / WC);
     const int y = (blockIdx.y * (NT / 32) + rowpair) * 2 + ((x + a.colour) & 1);
-#endif
     if (x >= W || y >= H || y >= c.y_limit) return;
     const int own = a.colour;
     const int pidx = y * W + x;
