@@ -327,6 +327,13 @@ def run_ours(args):
                 "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback"},
         "traffic": traffic,
     }
+    if args.blocksize == 11:
+        # texture-pipe view (the tighter bound): one wavefront per clock per SM; 9.65 wavefronts per
+        # warp-wide bilinear fetch measured by ncu (profiles/r01_variants_C2.json, independent of locality)
+        sm_count, clk_hz, wf_per_fetch = 148, 1.965e9, 9.65
+        tex_bound_ms = evals_checker * n_samp / 32.0 * wf_per_fetch / (sm_count * clk_hz) * 1e3
+        roofline["texture"] = {"bound": "texture wavefronts", "bound_ms": tex_bound_ms, "achieved_ms": avg_ms,
+                               "frac": tex_bound_ms / avg_ms if avg_ms else None, "wavefronts_per_fetch": wf_per_fetch}
     out = {
         "metric": "depthmaps/s", "value": value, "unit": "depthmaps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
