@@ -712,3 +712,13 @@ def test_cli_full_tsar_flow_with_detector(env, tmp_path):
     assert np.median(err_fill) < 0.01
     ground = (labels == 0) & (without > 0)
     assert np.mean(with_fill[ground] == without[ground]) > 0.95   # textured regions are left as PatchMatch found them
+
+
+def test_plain_c_program_runs_a_depthmap(env, tmp_path):
+    """examples/c_abi_check.c: a C11 program drives tsar_depthmap_host through the C ABI and recovers a known plane."""
+    import subprocess
+    from tests.test_cpu import _build_c_abi_check
+    exe = _build_c_abi_check(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "interior pixels" in r.stdout
