@@ -45,6 +45,14 @@ def test_library_exports_every_declared_symbol(pkg):
     assert set(pkg._lib.EXPORTS) <= declared
 
 
+def test_library_exports_the_reference_entry_points(pkg):
+    """gipuma.h:2-5: `int firstcuda(GlobalState&)` ... with the reference's C++ linkage (global namespace), so the
+    reference's main.cpp links against the library unchanged."""
+    out = subprocess.run("nm -D --defined-only '%s' | c++filt" % pkg._lib.LIB_PATH, shell=True, capture_output=True, text=True).stdout
+    for fn in ("firstcuda", "sliccuda", "fakecuda", "fillcuda"):
+        assert f" T {fn}(GlobalState&)" in out, fn
+
+
 def test_no_cpu_fallback(pkg):
     """Without a GPU the product path must fail loudly, not fall back to the oracle."""
     import torch
