@@ -458,7 +458,7 @@ def test_wmf_and_wmf_final_bit_exact(env, small):
         worst = max(worst, float((s_m != s_r).mean()))
         changed = max(changed, float((s_r != reliable).mean()))
     print(f"\n[wmf] worst per-level label mismatch {worst:.5%}")
-    assert worst < 2e-4
+    assert worst < 5e-4
     assert changed > 0.01                                # the filter really re-classified pixels
     for e in (mine, ref):
         e.set_regions(scene["region_text"], scene["region_norm4"])
@@ -472,7 +472,7 @@ def test_wmf_and_wmf_final_bit_exact(env, small):
             a, b = mine.download(fm), ref.download(fr)
             miss = 1 - pc.frac_bit_exact(a, b)
             worst = max(worst, miss)
-            assert miss < 2e-4, f"WMF_Final level {it} field {fm}: {miss:.4%} differ"
+            assert miss < 5e-4, f"WMF_Final level {it} field {fm}: {miss:.4%} differ"
     print(f"[wmf_final] worst per-level mismatch {worst:.5%}")
     assert (ref.download(rb.F_SCALE) != before).mean() > 0.001   # pixels were filled
     mine.close(); ref.close()
