@@ -204,7 +204,7 @@ def run_ours(args):
     eng.set_views_device([t.data_ptr() for t in imgs_dev], W, H, cams, scene["subset"], cam_f=scene["cam_f"])
     eng.set_params(params)
     eng.set_regions(scene["region_text"], scene["region_norm4"])
-    canny = scene["canny"]
+    canny = torch.from_numpy(np.ascontiguousarray(scene["canny"], np.float32)).pin_memory().numpy()   # pinned: e2e uploads it every step
     eng.upload(L.F_CANNY, canny)            # region labels of the reference view (caller input, resident)
 
     def step_resident(seed):
