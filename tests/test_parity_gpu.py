@@ -206,13 +206,15 @@ def test_edge_cases(env):
     """Odd sizes (last row outside the reference's checkerboard grid), V = 1 and V = 2, tiny images."""
     pkg, rb = env
     L = pkg._lib
-    cfg = dict(W=67, H=33, n_images=3, V=2, fx=150.0, radius=1.0, arc_deg=14.0)
-    scene = pkg.scene.make_scene(cfg)
-    params, mine, refs = pc.make_engines(pkg, scene, iterations=2, variants=("snapshot",))
-    ref = refs["snapshot"]
-    mine.depthmap(SEED); ref.depthmap(SEED, iters=2)
-    assert pc.frac_bit_exact(mine.download(L.F_NORM4), ref.download(rb.F_NORM4)) == 1.0
-    mine.close(); ref.close()
+    for W, H in ((67, 33), (261, 9), (9, 261), (33, 34), (64, 32)):   # odd, very wide, very tall, tile-aligned
+        cfg = dict(W=W, H=H, n_images=3, V=2, fx=150.0, radius=1.0, arc_deg=14.0)
+        scene = pkg.scene.make_scene(cfg)
+        params, mine, refs = pc.make_engines(pkg, scene, iterations=2, variants=("snapshot",))
+        ref = refs["snapshot"]
+        mine.depthmap(SEED); ref.depthmap(SEED, iters=2)
+        assert pc.frac_bit_exact(mine.download(L.F_NORM4), ref.download(rb.F_NORM4)) == 1.0, (W, H)
+        assert pc.frac_bit_exact(mine.download(L.F_COST), ref.download(rb.F_COST)) == 1.0, (W, H)
+        mine.close(); ref.close()
 
 
 def test_non_8bit_images_use_fp32_textures(env):
