@@ -308,8 +308,16 @@ def run_all_views(opt, mslp):
         done.append(r)
         return r
 
-    def lane_worker(j):                                         # one host thread per lane: a context is never shared
-        for k in range(j, len(mine), len(lanes)):
+    import itertools
+    import threading
+    ticket, ticket_lock = itertools.count(), threading.Lock()
+
+    def lane_worker(j):     # one host thread per lane (a context is never shared); views are taken from a shared queue,
+        while True:         # so lanes stay balanced when the views' neighbour counts differ
+            with ticket_lock:
+                k = next(ticket)
+            if k >= len(mine):
+                return
             process(k, lanes[j])
 
     with cf.ThreadPoolExecutor(len(lanes)) as ex:
