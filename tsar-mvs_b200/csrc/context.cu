@@ -165,6 +165,12 @@ static int rebuild_constants(tsar_ctx *ctx) {
         for (int k = 0; k < 9; k++) { c.view[i].R[k] = s.R[k]; c.view[i].K[k] = s.K[k]; }
         for (int k = 0; k < 3; k++) c.view[i].t[k] = s.t4[k];
     }
+    // zero-skew pinhole intrinsics everywhere? (lets the homography skip the products with exact zeros)
+    auto pinhole = [](const float *K) { return K[1] == 0.f && K[3] == 0.f && K[6] == 0.f && K[7] == 0.f && K[8] == 1.f; };
+    c.k_pinhole = pinhole(r.K_inv) ? 1 : 0;
+    for (int i = 0; i < ctx->V && c.k_pinhole; i++) c.k_pinhole = pinhole(c.view[i].K) ? 1 : 0;
+    const char *nk = getenv("TSAR_B200_NO_PINHOLE_FASTPATH");
+    if (nk && nk[0] == '1') c.k_pinhole = 0;
     ctx->pm_init = c;
     fill_window(ctx->pm_init, ctx->params.box_hsize, ctx->params.box_vsize, true);
     ctx->variant = pick_variant(ctx->params, false);

@@ -44,6 +44,8 @@ struct PmConst {
     int n_best, cost_comb;
     int y_limit;           // rows the reference's checkerboard grid reaches (gipuma.cu:1721)
     int rng_pitch;
+    int k_pinhole;         // 1: all intrinsics (and K_ref^-1) are zero-skew pinhole matrices with a unit last row (host-side
+                           // dispatch to the PIN = true instantiation of the checkerboard kernel)
     float Kinv[9];         // cameras[0].K_inv
     float Minv[9];         // cameras[0].M_inv
     float Pc[3];           // cameras[0].P_col34
@@ -137,6 +139,7 @@ __device__ __forceinline__ RefStats window_weights(const PmConst &c, const float
 // ---------------------------------------------------------------------------------------------
 // plane-induced homography H = K_src (R - t n^T / d) K_ref^-1   (getHomography_cu, gipuma.cu:207-224)
 // ---------------------------------------------------------------------------------------------
+template <bool PIN>
 __device__ __forceinline__ void homography(const PmConst &c, const ViewC &v, const float4 &pl, float *__restrict__ Hm) {
     float A[9];
     const float n[3] = {pl.x, pl.y, pl.z};
@@ -155,6 +158,26 @@ __device__ __forceinline__ void homography(const PmConst &c, const ViewC &v, con
             for (int q = 0; q < 3; q++) A[i * 3 + q] = fsub(v.R[i * 3 + q], fdiv(fmul(v.t[i], n[q]), pl.w));
     }
     float T[9];
+    if (PIN) {
+        // Every intrinsic matrix is [[fx,0,cx],[0,fy,cy],[0,0,1]] (and K_ref^-1 has the same zero pattern): the products
+        // with the exact zeros contribute +-0 and the one with 1 is exact, so they are dropped.  The remaining
+        // operations are the reference's, in its order; only the sign of an exactly-zero entry can differ, which no
+        // later operation observes (entries are only multiplied by pixel coordinates and added to non-zero terms, or
+        // compared by magnitude).
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            T[r * 3 + 0] = fmul(A[r * 3 + 0], c.Kinv[0]);
+            T[r * 3 + 1] = fmul(A[r * 3 + 1], c.Kinv[4]);
+            T[r * 3 + 2] = dot3(A[r * 3 + 0], c.Kinv[2], A[r * 3 + 1], c.Kinv[5], A[r * 3 + 2], c.Kinv[8]);
+        }
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            Hm[0 * 3 + q] = ffma(v.K[2], T[2 * 3 + q], fmul(v.K[0], T[0 * 3 + q]));
+            Hm[1 * 3 + q] = ffma(v.K[5], T[2 * 3 + q], fmul(v.K[4], T[1 * 3 + q]));
+            Hm[2 * 3 + q] = T[2 * 3 + q];
+        }
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -185,11 +208,11 @@ __device__ __forceinline__ void homography(const PmConst &c, const ViewC &v, con
 // window sums are carried in units of N (i.e. scaled by 2^8 / 2^16, exact in binary floating point) and
 // scaled back once per evaluation, so costs are bit-identical to the fp32-texture path while each warp-wide
 // fetch moves a quarter of the texel bytes through the L1TEX data pipe (the measured limiter).
-template <int NT, int N1, bool PXF, bool U8, class WS>
+template <int NT, int N1, bool PXF, bool U8, bool PIN, class WS>
 __device__ __forceinline__ float view_cost(const PmConst &c, int vi, int x, int y, const float4 &pl,
                                            const WS &ws, const RefStats &rs) {
     float Hm[9];
-    homography(c, c.view[vi], pl, Hm);
+    homography<PIN>(c, c.view[vi], pl, Hm);
     const cudaTextureObject_t tex = U8 ? c.tex8[vi] : c.tex[vi];
     float s_s = 0.f, s_ss = 0.f, s_rs = 0.f;
     const int n1x = N1 ? N1 : c.n1x, n1y = N1 ? N1 : c.n1y;
@@ -282,7 +305,7 @@ struct MvResult {
 // GENERIC = false: only the two smallest costs are ever read (cost_comb == COMB_BEST_N and
 // n_best <= 2, the setting of every run script), kept in registers.  GENERIC = true: any n_best /
 // COMB_ALL through the reference's full insertion sort (local-memory arrays, as the reference).
-template <int NT, int N1, bool GENERIC, bool PXF = false, bool U8 = false, class WS = WPair<NT>>
+template <int NT, int N1, bool GENERIC, bool PXF = false, bool U8 = false, bool PIN = false, class WS = WPair<NT>>
 __device__ __forceinline__ MvResult multiview_cost(const PmConst &c, int x, int y, const float4 &pl,
                                                    const WS &ws, const RefStats &rs) {
     MvResult out;
@@ -290,7 +313,7 @@ __device__ __forceinline__ MvResult multiview_cost(const PmConst &c, int x, int 
         float s0 = __int_as_float(0x7f800000), s1 = __int_as_float(0x7f800000);
         int nvalid = 0, bidx = -1;
         for (int vi = 0; vi < c.V; vi++) {
-            float cv = view_cost<NT, N1, PXF, U8>(c, vi, x, y, pl, ws, rs);
+            float cv = view_cost<NT, N1, PXF, U8, PIN>(c, vi, x, y, pl, ws, rs);
             if (cv < kMaxCost) nvalid++;
             else cv = kMaxCost;
             if (cv < s0) { s1 = s0; s0 = cv; bidx = vi; }
@@ -313,7 +336,7 @@ __device__ __forceinline__ MvResult multiview_cost(const PmConst &c, int x, int 
         float cv[kMaxViews], orig[kMaxViews];
         int nvalid = 0;
         for (int vi = 0; vi < c.V; vi++) {
-            float v = view_cost<NT, N1, PXF, U8>(c, vi, x, y, pl, ws, rs);
+            float v = view_cost<NT, N1, PXF, U8, PIN>(c, vi, x, y, pl, ws, rs);
             if (v < kMaxCost) nvalid++;
             else v = kMaxCost;
             cv[vi] = v; orig[vi] = v;

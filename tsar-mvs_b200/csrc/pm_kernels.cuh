@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_init_kernel(const __grid_constant
 // colours), the thread's own result goes to `*_out` (which may alias `*_in` when DO_SP is false).
 // ---------------------------------------------------------------------------------------------
 
-template <int NT, int MINB, int N1, bool GEN, bool U8, bool DO_SP, bool DO_PR, bool TILE>
+template <int NT, int MINB, int N1, bool GEN, bool U8, bool DO_SP, bool DO_PR, bool TILE, bool PIN>
 __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_constant__ PmConst c,
                                                         const float *__restrict__ ref, const CheckerArgs a) {
     static_assert(!TILE || N1 > 0, "the tile layout needs a compile-time window");
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
             deltaN = fmul(deltaN, 0.25f);
         }
         if (eval) {
-            const MvResult r = multiview_cost<NT, N1, GEN, false, U8>(c, x, y, cand, wt, rs);
+            const MvResult r = multiview_cost<NT, N1, GEN, false, U8, PIN>(c, x, y, cand, wt, rs);
             if (r.cost < cost_now) {
                 cost_now = r.cost; norm_now = cand; ratio_now = r.ratio; beview_now = r.beview; meta_dirty = true;
                 depth_now = cand_depth;  // only read by the refinement rounds
