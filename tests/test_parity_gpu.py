@@ -149,6 +149,27 @@ def test_fused_equals_unfused(env, small, monkeypatch):
     assert n_u > n_f > 0
 
 
+def test_general_intrinsics_instantiation_matches(env, small, monkeypatch):
+    """The homography instantiation for arbitrary intrinsic matrices (selected automatically when some K has skew or
+    a non-unit last row; forced here) and the zero-skew pinhole one give the same bits, and both equal the reference."""
+    pkg, rb = env
+    L = pkg._lib
+    params, fast, refs = pc.make_engines(pkg, small, iterations=2, variants=("snapshot",))
+    fast.depthmap(SEED)
+    o_f = fast.download(L.F_NORM4)
+    monkeypatch.setenv("TSAR_B200_NO_PINHOLE_FASTPATH", "1")
+    params, general, _ = pc.make_engines(pkg, small, iterations=2, variants=())
+    general.depthmap(SEED)
+    o_g = general.download(L.F_NORM4)
+    monkeypatch.delenv("TSAR_B200_NO_PINHOLE_FASTPATH")
+    refs["snapshot"].depthmap(SEED, iters=2)
+    o_r = refs["snapshot"].download(rb.F_NORM4)
+    for e in (fast, general, refs["snapshot"]):
+        e.close()
+    assert pc.frac_bit_exact(o_f, o_g) == 1.0
+    assert pc.frac_bit_exact(o_g, o_r) == 1.0
+
+
 def test_run_is_deterministic(env, small):
     pkg, rb = env
     params, mine, _ = pc.make_engines(pkg, small, iterations=2, variants=())
