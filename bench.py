@@ -150,6 +150,15 @@ def workload_name(cfg_name, cfg, iters, box=11):
             f"confidence + textureless depth completion)")
 
 
+def config_dict(cfg_name, cfg, iters, box, world):
+    """`config` of the JSON line: the SAME dict in both arms (the driver compares them key by key)."""
+    work_bytes = (cfg["n_images"] * 5 + 72) * cfg["W"] * cfg["H"]
+    timing = (f"inputs_larger_than_l2 ({work_bytes / 1e6:.0f} MB of views + state per step)" if work_bytes >= (512 << 20)
+              else "l2_flush (256 MB overwritten between timed steps)")
+    return {"workload": workload_name(cfg_name, cfg, iters, box), "timing": timing, "reference_views_per_gpu_per_step": 1,
+            "parallelism": f"views sharded over {world} GPU(s), one reference-view stream per GPU, no collective on the data path"}
+
+
 def build_scene(pkg, cfg_name, rank, device):
     import torch
     scene = pkg.scene.make_scene(cfg_name, with_colour=True, ref_index=rank, backend="torch", device=device)
@@ -314,15 +323,15 @@ def run_ours(args):
     roofline = {
         "bound": "fp32", "kernel": "pm_checker_kernel (fused red/black propagation + refinement)",
         "achieved": achieved, "peak": ffma_tf, "unit": "TFLOP/s", "frac": achieved / ffma_tf if ffma_tf else None,
-        "peak_source": "FP32 FFMA issue microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry); "
-                       f"nominal {FP32_NOMINAL_TFLOPS} TFLOP/s",
+        "peak_source": "FP32 FFMA issue microbenchmark measured live in this run (tsar_dbg_peaks; MEASURED_PEAKS.json has no FP32 entry); "
+                       f"recorded with clocks in profiles/r02_fp32_peaks.json; nominal {FP32_NOMINAL_TFLOPS} TFLOP/s",
         "frac_of_nominal": achieved / FP32_NOMINAL_TFLOPS,
         "algorithmic_flops_per_launch": evals_checker * flops_eval, "avg_launch_ms": avg_ms, "launches_timed": chk_n,
         "kernel_share_of_step": chk_ms / ms_local if ms_local else None,
         "gevals_per_s": evals_checker / (avg_ms * 1e-3) / 1e9,
         "tex_gsamples_per_s": evals_checker * n_samp / (avg_ms * 1e-3) / 1e9, "tex_peak_gsamples_per_s": tex_g,
         "tex_frac": (evals_checker * n_samp / (avg_ms * 1e-3) / 1e9) / tex_g if tex_g else None,
-        "mufu_peak_gops_measured_lower_bound": mufu_g,
+        "mufu_peak_gops_measured": mufu_g, "mufu_peak_gops_nominal": 148 * 16 * 1.965,
         "hbm": {"bound": "hbm", "achieved": alg_bytes / (avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback"},
         "traffic": traffic,
@@ -338,8 +347,7 @@ def run_ours(args):
         "metric": "depthmaps/s", "value": value, "unit": "depthmaps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "ours",
-        "config": {"workload": workload_name(args.config, cfg, iters, args.blocksize), "timing": (f"inputs_larger_than_l2 ({work_bytes / 1e6:.0f} MB of views + state per step)" if flush is None
-                              else "l2_flush (256 MB overwritten between timed steps)"), "reference_views_per_gpu_per_step": 1, "parallelism": f"views sharded over {world} GPU(s)"},
+        "config": config_dict(args.config, cfg, iters, args.blocksize, world),
         "gevals_per_s": world * args.steps * n_evals / (ms * 1e-3) / 1e9, "evals_per_depthmap": n_evals,
         "roofline": roofline, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
     }
@@ -353,10 +361,10 @@ def run_ours(args):
 
 
 def run_reference(args):
-    """The reference's own kernels (oracle/_ref) on the same workload; rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+    """The reference's own kernels (oracle/_ref) on the same workload.  The reference's execution model is one process
+    per reference view on one GPU (scripts/pipes.sh:30-49), so under torchrun EVERY rank runs its own stream of reference
+    views on its own GPU, exactly like our arm; the time is the max over ranks and rank 0 prints the line.  Nothing of
+    libtsar_b200.so is loaded here: struct layouts and the closed-form evaluation count are pure Python."""
     # the reference kernels printf debug lines ("after prop : ...", gipuma.cu:1043-1045): keep stdout for the JSON line
     sys.stdout.flush()
     real_stdout = os.dup(1)
@@ -370,13 +378,17 @@ def run_reference(args):
     import __graft_entry__ as g
     pkg = g.load_package()
     from oracle import ref_binding as rb
+    rank, world, local = dist_setup(args.gpus)
     if not rb.available("asis"):
-        emit({"impl": "reference", "unavailable": "oracle/_ref/libtsar_ref.so missing (run `make oracle` where the reference checkout exists)"})
+        if rank == 0:
+            emit({"impl": "reference", "unavailable": "oracle/_ref/libtsar_ref.so missing (run `make oracle` where the reference checkout exists)"})
+        shutdown(world)
         return
-    torch.cuda.set_device(0)
     cfg = pkg.scene.CONFIGS[args.config]
     iters = 8
-    scene, imgs_dev, imgs_host, bgrx = build_scene(pkg, args.config, 0, "cuda:0")
+    scene, imgs_dev, imgs_host, bgrx = build_scene(pkg, args.config, rank, f"cuda:{local}")
+    del imgs_dev
+    torch.cuda.empty_cache()
     from tsar_mvs_b200.engine import cameras_to_struct
     cams = cameras_to_struct(scene["cams"])
     params = pkg.make_params(box=args.blocksize, iterations=iters, n_best=1, cost_comb=1, min_disparity=scene["min_disparity"],
@@ -395,35 +407,41 @@ def run_reference(args):
 
     for _ in range(args.warmup):
         step(SEED)
-    torch.cuda.synchronize()
-    with ClockSampler(0) as clk:
-        t0 = time.perf_counter()
+    barrier(world)
+    # the reference launches on the legacy default stream, which is torch's current stream here
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
+        e0.record()
         for k in range(args.steps):
             step(SEED + 100 * k)
+        e1.record()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-    value = args.steps / dt
-    # evaluation count by the same closed form
-    eng = pkg.DepthmapEngine(0)
-    eng.set_views_device([t.data_ptr() for t in imgs_dev], cfg["W"], cfg["H"], cams, scene["subset"], cam_f=scene["cam_f"])
-    eng.set_params(params)
-    n_evals = eng.eval_count(iters)
-    eng.close()
+    ms_local = e0.elapsed_time(e1)
+    barrier(world)
+    ms = max_over_ranks(ms_local, world)
+    ref.close()
+    torch.cuda.synchronize()
+    if rank != 0:
+        shutdown(world)
+        return
+    value = world * args.steps / (ms * 1e-3)
+    n_evals = pkg.counts.eval_count(cfg["W"], cfg["H"], cfg["V"], iters, scene["max_disparity"])
     out = {
-        "metric": "depthmaps/s", "value": value, "unit": "depthmaps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "metric": "depthmaps/s", "value": value, "unit": "depthmaps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": workload_name(args.config, cfg, iters, args.blocksize), "note": "reference CUDA kernels rebuilt for sm_100a (gipuma.cu + gSLICr "
-                   "unmodified), managed memory, device sync after every kernel, warm (pages resident after warm-up); the reference has no CPU path"},
-        "gevals_per_s": args.steps * n_evals / dt / 1e9,
+        "config": config_dict(args.config, cfg, iters, args.blocksize, world),
+        "reference_note": "reference CUDA kernels rebuilt for sm_100a (gipuma.cu + gSLICr unmodified), managed memory, device sync after "
+                          "every kernel, warm (pages resident after warm-up); one process + one GPU per reference-view stream as in "
+                          "scripts/pipes.sh; the reference has no CPU path",
+        "gevals_per_s": world * args.steps * n_evals / (ms * 1e-3) / 1e9, "evals_per_depthmap": n_evals,
         "cpu_baseline": {"value": value, "unit": "depthmaps/s", "cores": 0, "kind": "reference",
-                         "sample": f"{args.steps} full depthmaps of the workload on one B200 (the reference implements this path in CUDA only)"},
+                         "sample": f"{args.steps} full depthmaps of the workload per GPU on {world} B200 (the reference implements this path in CUDA only)"},
         "e2e": {"value": value, "unit": "depthmaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "clocks": clk.summary(),
     }
-    ref.close()
-    torch.cuda.synchronize()
     emit(out)
+    shutdown(world)
 
 
 if __name__ == "__main__":

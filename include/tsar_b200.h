@@ -223,6 +223,13 @@ int tsar_dbg_peaks(tsar_ctx *ctx, float *out3);
 /* Experiment: samples + bilinear fetch rate of the same image stored as f32 / u8-unorm / u16-unorm / f16 texels
  * (out = 4*n floats, rate4 = Gsamples/s per format). */
 int tsar_dbg_tex_formats(tsar_ctx *ctx, int image, int n, const float *xy, float *out, float *rate4);
+/* Device-side counter of the propagation candidates of the checkerboard launch of `colour` that would run on the
+ * current state: out = 22 counters -- pixels of the colour, candidates behind their border guards
+ * (the closed form of tsar_eval_count), candidates inside the depth range (= cost evaluations the reference executes,
+ * per source view), bitwise duplicates of the pixel's own plane, duplicates of an earlier candidate of the same pixel,
+ * distinct candidates; warp-wide evaluation rounds as written / with per-lane lists of distinct candidates / perfectly
+ * packed; warps; the same three figures without the own-plane rule; then pixels by number of distinct candidates 0..8. */
+int tsar_dbg_candidate_stats(tsar_ctx *ctx, int colour, unsigned long long *out22);
 /* Test-only: tsar_eval_planes normally rounds H*(x,y,1) as the reference's real kernels do
  * (fma(m0,x, m1*y) + m2).  The oracle's stand-alone wrapper kernel around pmCostMultiview_cu is compiled
  * by nvcc with the loop-hoisted form (fma(m1,y, m0*x) + m2); wrapper_rounding=1 selects that form so the

@@ -51,7 +51,7 @@ EXPORTS = [
     "tsar_init_planes", "tsar_load_planes", "tsar_launch", "tsar_iterate", "tsar_eval_planes", "tsar_lrdiff",
     "tsar_getview", "tsar_get_disp", "tsar_update_scale_2", "tsar_update_scale", "tsar_compute_disp", "tsar_wmf",
     "tsar_wmf_final", "tsar_set_regions", "tsar_fit_region_planes", "tsar_ransac_rand_per_region", "tsar_upload", "tsar_download", "tsar_device_ptr", "tsar_depthmap",
-    "tsar_depthmap_host", "tsar_slic", "tsar_launch_count", "tsar_eval_count", "tsar_version", "tsar_dbg_tex_sample", "tsar_dbg_peaks", "tsar_dbg_eval_rounding", "tsar_dbg_tex_formats", "tsar_profile", "tsar_profile_read",
+    "tsar_depthmap_host", "tsar_slic", "tsar_launch_count", "tsar_eval_count", "tsar_version", "tsar_dbg_tex_sample", "tsar_dbg_peaks", "tsar_dbg_eval_rounding", "tsar_dbg_candidate_stats", "tsar_dbg_tex_formats", "tsar_profile", "tsar_profile_read",
     "tsar_weak_edges", "tsar_weak_connect", "tsar_weak_boundary", "tsar_weak_close_border", "tsar_weak_regions", "tsar_set_labels_quarter",
 ]
 
@@ -106,6 +106,7 @@ def load():
         "tsar_dbg_tex_sample": (i, [vp, i, i, vp, vp]),
         "tsar_dbg_peaks": (i, [vp, fp]),
         "tsar_dbg_eval_rounding": (i, [vp, i]),
+        "tsar_dbg_candidate_stats": (i, [vp, i, vp]),
         "tsar_dbg_tex_formats": (i, [vp, i, i, vp, vp, vp]),
         "tsar_profile": (i, [vp, i]),
         "tsar_profile_read": (i, [vp, fp, ip]),

@@ -1032,6 +1032,23 @@ int tsar_profile_read(tsar_ctx *ctx, float *checker_ms_total, int *n_launches) {
     return TSAR_OK;
 }
 
+int tsar_dbg_candidate_stats(tsar_ctx *ctx, int colour, unsigned long long *out) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (!out || colour < 0 || colour > 1) FAIL(TSAR_ERR_ARG, "bad candidate-statistics arguments");
+    if (!ctx->have_planes) FAIL(TSAR_ERR_STATE, "no planes: call tsar_init_planes or tsar_load_planes first");
+    if ((rc = ensure_scratch(ctx, kCandStatWords * sizeof(unsigned long long)))) return rc;
+    CheckerArgs a{};
+    for (int col = 0; col < 2; col++) { a.plane_in[col] = ctx->plane[ctx->cur[col]]; a.cost_in[col] = ctx->cost[ctx->cur[col]]; }
+    a.colour = colour;
+    CK(cudaMemsetAsync(ctx->scratch, 0, kCandStatWords * sizeof(unsigned long long), ctx->stream));
+    CK(pm_launch_cand_stats(ctx->pm, a, (unsigned long long *)ctx->scratch, ctx->stream));
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, ctx->scratch, kCandStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSAR_OK;
+}
+
 int tsar_dbg_eval_rounding(tsar_ctx *ctx, int wrapper_rounding) {
     if (!ctx) return TSAR_ERR_ARG;
     ctx->eval_wrapper_rounding = wrapper_rounding ? 1 : 0;
@@ -1122,7 +1139,7 @@ int tsar_dbg_peaks(tsar_ctx *ctx, float *out3) {
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         CK(cudaEventSynchronize(ctx->ev1));
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        best[1] = std::max(best[1], (float)((double)blocks * threads * (iters / 4) * 8 * 4 / (ms * 1e-3) / 1e9));
+        best[1] = std::max(best[1], (float)((double)blocks * threads * (iters / 4) * 8 * 8 / (ms * 1e-3) / 1e9));
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
         dbg_tex_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->tex[0], (float *)ctx->scratch, iters / 16, ctx->W, ctx->H);
         CK(cudaEventRecord(ctx->ev1, ctx->stream));

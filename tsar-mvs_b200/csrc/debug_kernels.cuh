@@ -24,18 +24,24 @@ __global__ void __launch_bounds__(256) dbg_ffma_kernel(float *out, int iters, fl
     if (r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7 == 12345.678f) out[0] = r0;
 }
 
+// 8 independent MUFU.RSQ chains per thread (rsqrt is not an involution, so nothing can be folded away -- the first
+// version chained rcp(rcp(x)) and the compiler removed the whole loop): 8 x 8 = 64 MUFU per round per thread
+__device__ __forceinline__ float dbg_rsq(float v) {
+    float r;
+    asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 __global__ void __launch_bounds__(256) dbg_mufu_kernel(float *out, int iters) {
-    float r0 = threadIdx.x * 1e-3f, r1 = r0 + .1f, r2 = r0 + .2f, r3 = r0 + .3f;
+    float r0 = 1.0f + threadIdx.x * 1e-3f, r1 = r0 + .1f, r2 = r0 + .2f, r3 = r0 + .3f, r4 = r0 + .4f, r5 = r0 + .5f, r6 = r0 + .6f,
+          r7 = r0 + .7f;
     for (int i = 0; i < iters; i++) {
 #pragma unroll 8
         for (int k = 0; k < 8; k++) {
-            asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(r0));
-            asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(r1));
-            asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(r2));
-            asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(r3));
+            r0 = dbg_rsq(r0); r1 = dbg_rsq(r1); r2 = dbg_rsq(r2); r3 = dbg_rsq(r3);
+            r4 = dbg_rsq(r4); r5 = dbg_rsq(r5); r6 = dbg_rsq(r6); r7 = dbg_rsq(r7);
         }
     }
-    if (r0 + r1 + r2 + r3 == 12345.678f) out[0] = r0;
+    if (r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7 == 12345.678f) out[0] = r0;
 }
 
 // bilinear fp32 fetches with warp-local coordinates (like a warped window): `iters` x 4 TEX per thread

@@ -5,6 +5,7 @@
 
 #include "pm_core.cuh"
 #include "pm_launch.h"
+#include "pm_neighbours.cuh"
 
 // Kernels are templates; two translation units that instantiate the same template arguments with different macro
 // settings (PM_FAST_UNROLL, PM_WARP_COLS) would otherwise share one symbol and silently run the same code.  Each
@@ -164,88 +165,9 @@ __global__ void __launch_bounds__(NT, MINB) pm_checker_kernel(const __grid_const
         float cand_depth = 0.f;
         bool eval = false;
         if (step < 8) {
-            // -- pick the neighbour whose plane is tried at this pixel
-            float cmin;
-            int best = -1;
-            bool bown = false;
-            switch (step) {
-                case 0:  // up_far: 11 samples, stride 2, opposite colour
-                    if (y > 2) {
-                        best = pidx - 3 * W; cmin = cO[best];
-#pragma unroll
-                        for (int i = 1; i < 11; i++)
-                            if (y > 2 + 2 * i) { const int pt = pidx - (3 + 2 * i) * W; const float v = cO[pt]; if (v < cmin) { cmin = v; best = pt; } }
-                    }
-                    break;
-                case 1:  // down_far: the running minimum starts from c[up_far]; out of bounds for
-                         // y < 3, where the reference reads the zero guard (Q5)
-                    if (y < H - 3) {
-                        cmin = (y >= 3) ? cO[pidx - 3 * W] : 0.0f;
-                        best = pidx + 3 * W;
-#pragma unroll
-                        for (int i = 1; i < 11; i++)
-                            if (y < H - 3 - 2 * i) { const int pt = pidx + (3 + 2 * i) * W; const float v = cO[pt]; if (v < cmin) { cmin = v; best = pt; } }
-                    }
-                    break;
-                case 2:  // left_far
-                    if (x > 2) {
-                        best = pidx - 3; cmin = cO[best];
-#pragma unroll
-                        for (int i = 1; i < 11; i++)
-                            if (x > 2 + 2 * i) { const int pt = pidx - 3 - 2 * i; const float v = cO[pt]; if (v < cmin) { cmin = v; best = pt; } }
-                    }
-                    break;
-                case 3:  // right_far: comparison inverted in the reference (tracks the maximum, Q6)
-                    if (x < W - 3) {
-                        best = pidx + 3; cmin = cO[best];
-#pragma unroll
-                        for (int i = 1; i < 11; i++)
-                            if (x < W - 3 - 2 * i) { const int pt = pidx + 3 + 2 * i; const float v = cO[pt]; if (cmin < v) { cmin = v; best = pt; } }
-                    }
-                    break;
-                // near "V" areas: the direct neighbour (opposite colour) + same-colour extras, which are read
-                // from the pre-launch snapshot (gipuma.cu:952-1042)
-                case 4:  // up_near
-                    if (y > 0) {
-                        best = pidx - W; cmin = cO[best];
-#pragma unroll
-                        for (int i = 0; i < 3; i++) {
-                            if (y > 1 + i && x > i) { const int pt = pidx - (2 + i) * W - i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-                            if (y > 1 + i && x < W - 1 - i) { const int pt = pidx - (2 + i) * W + i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-                        }
-                    }
-                    break;
-                case 5:  // down_near
-                    if (y < H - 1) {
-                        best = pidx + W; cmin = cO[best];
-#pragma unroll
-                        for (int i = 0; i < 3; i++) {
-                            if (y < H - 2 - i && x > i) { const int pt = pidx + (2 + i) * W - i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-                            if (y < H - 2 - i && x < W - 1 - i) { const int pt = pidx + (2 + i) * W + i; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-                        }
-                    }
-                    break;
-                case 6:  // left_near
-                    if (x > 0) {
-                        best = pidx - 1; cmin = cO[best];
-#pragma unroll
-                        for (int i = 0; i < 3; i++) {
-                            if (x > 1 + i && y > i) { const int pt = pidx - (2 + i) - i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-                            if (x > 1 + i && y < H - 1 - i) { const int pt = pidx - (2 + i) + i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-                        }
-                    }
-                    break;
-                default:  // 7: right_near
-                    if (x < W - 1) {
-                        best = pidx + 1; cmin = cO[best];
-#pragma unroll
-                        for (int i = 0; i < 3; i++) {
-                            if (x < W - 2 - i && y > i) { const int pt = pidx + (2 + i) - i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-                            if (x < W - 2 - i && y < H - 1 - i) { const int pt = pidx + (2 + i) + i * W; const float v = cS[pt]; if (v < cmin) { cmin = v; best = pt; bown = true; } }
-                        }
-                    }
-                    break;
-            }
+            // -- pick the neighbour whose plane is tried at this pixel (pm_neighbours.cuh)
+            bool bown;
+            const int best = pick_neighbour(step, x, y, W, H, pidx, cO, cS, bown);
             if (best >= 0) {
                 // spatialPropagation_cu (gipuma.cu:525-566).  The cost has no side effect, so it is skipped when
                 // the depth-range test would reject the plane anyway.

@@ -41,6 +41,13 @@ cudaError_t pm_launch_rng_table(uint32_t *table, int pitch, int H, int len, unsi
 constexpr int kRngBatchMax = 64;
 cudaError_t pm_launch_rng_tables(uint32_t *tables, size_t stride, int n_tables, const unsigned long long *seeds, int pitch, int H,
                                  int len, cudaStream_t);
+// candidate statistics of the checkerboard launch that would run on this state (debug instrumentation, pm_misc.cu)
+constexpr int kCandStatHist = 13;    // out[13 .. 21]: pixels by number of distinct, not-own candidates (0..8)
+constexpr int kCandStatWords = 22;   // out[0..12]: pixels, candidates behind the border guards, in depth range (= executed
+                                     // evaluations / V), duplicates of the own plane, duplicates of an earlier candidate,
+                                     // distinct; warp rounds today, with per-lane compaction, with perfect packing; warps;
+                                     // the same three without the own-plane rule (distinct2 sum, max, packed)
+cudaError_t pm_launch_cand_stats(const PmConst &c, const CheckerArgs &a, unsigned long long *out, cudaStream_t s);
 cudaError_t pm_launch_merge_colour(int W, int H, int colour, const float4 *psrc, const float *csrc, float4 *pdst,
                                    float *cdst, cudaStream_t);
 

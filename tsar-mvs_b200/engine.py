@@ -224,6 +224,18 @@ class DepthmapEngine:
         self._ck(self.lib.tsar_profile_read(self.h, C.byref(ms), C.byref(n)), "tsar_profile_read")
         return ms.value, n.value
 
+    def candidate_stats(self, colour):
+        """Counters of the propagation candidates the checkerboard launch of `colour` would try on the current state
+        (tsar_dbg_candidate_stats): dict of counts + histogram of distinct candidates per pixel."""
+        out = (C.c_ulonglong * 22)()
+        self._ck(self.lib.tsar_dbg_candidate_stats(self.h, int(colour), out), "tsar_dbg_candidate_stats")
+        names = ("pixels", "behind_border_guards", "in_depth_range", "dup_of_own_plane", "dup_of_earlier_candidate", "distinct",
+                 "warp_rounds_as_written", "warp_rounds_lane_lists", "warp_rounds_packed", "warps", "distinct_without_own_rule",
+                 "warp_rounds_lane_lists_without_own_rule", "warp_rounds_packed_without_own_rule")
+        d = {n: int(out[k]) for k, n in enumerate(names)}
+        d["pixels_by_distinct"] = [int(out[13 + k]) for k in range(9)]
+        return d
+
     def peaks(self):
         """Issue-rate microbenchmarks: (FP32 FFMA TFLOP/s, MUFU Gop/s, bilinear texture Gsamples/s)."""
         out = (C.c_float * 3)()
