@@ -9,7 +9,7 @@ PKG       := tsar-mvs_b200
 SRC       := $(PKG)/csrc
 BUILD     := build/obj
 OBJS      := $(BUILD)/context.o $(BUILD)/pm_inst_w11.o $(BUILD)/pm_inst_w19.o $(BUILD)/pm_inst_generic.o \
-             $(BUILD)/pm_misc.o $(BUILD)/gipuma_shim.o $(BUILD)/weak_texture.o
+             $(BUILD)/pm_misc.o $(BUILD)/gipuma_shim.o $(BUILD)/gslicr_shim.o $(BUILD)/weak_texture.o
 HDRS      := $(wildcard $(SRC)/*.cuh $(SRC)/*.h $(SRC)/*.inc include/*.h)
 
 all: $(PKG)/libtsar_b200.so

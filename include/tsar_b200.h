@@ -158,6 +158,19 @@ int tsar_set_regions(tsar_ctx *ctx, int n_regions, const float *text, const floa
 int tsar_fit_region_planes(tsar_ctx *ctx, int n_regions, const float *region_text, const float *region_size,
                            const uint32_t *rnd, float *region_norm4);
 int tsar_ransac_rand_per_region(void);
+/* Same fit with the rand() stream generated on the device from `seed` (no 46 000-value host array per region): value i of
+ * region r is tsar_ransac_rand_value(seed, r, i), a counter-based stream of non-negative 31-bit integers.  The reference
+ * never seeds rand(), so any stream is as faithful as another; this one is reproducible. */
+int tsar_fit_region_planes_seeded(tsar_ctx *ctx, int n_regions, const float *region_text, const float *region_size,
+                                  uint64_t seed, float *region_norm4);
+uint32_t tsar_ransac_rand_value(uint64_t seed, int region, int index);
+
+/* lines->scale (the "reliable pixel" flags the RANSAC fit and WMF read).  The shipped flow fills it on the host from APD's
+ * weak.png: 1 where the pixel is white, green or red (main.cpp:1499-1514) -- tsar_scale_from_weak_png does that on the
+ * device from the decoded W*H BGR bytes (host pointer).  When PatchMatch runs inside the library there is no weak.png;
+ * tsar_scale_from_confidence sets scale = (confid > threshold) from gipuma_getview's confidence instead. */
+int tsar_scale_from_weak_png(tsar_ctx *ctx, const unsigned char *bgr);
+int tsar_scale_from_confidence(tsar_ctx *ctx, float threshold);
 
 /* ---- weak-texture region detector: texture() in main.cpp:365-596 --------------------
  * Host functions (sequential raster scans whose results depend on the scan order; the reference runs them on the
@@ -183,6 +196,11 @@ int tsar_set_labels_quarter(tsar_ctx *ctx, const int *labels, int wq, int hq);
 /* ---- state transfer --------------------------------------------------------------------------- */
 int tsar_upload(tsar_ctx *ctx, int field, const void *host_src, size_t bytes);
 int tsar_download(tsar_ctx *ctx, int field, void *host_dst, size_t bytes);
+/* The payloads of the reference's output files after gipuma_compute_disp (main.cpp:1785-1861): depth (W*H floats,
+ * TSAR_disp.dmb), normals (W*H*3 floats, TSAR_normals.dmb) and the confidence map (W*H floats; computed but never
+ * written by the reference).  The output layout is split on the device; host pointers (pinned memory makes the copies
+ * asynchronous to other streams); any of them may be NULL. */
+int tsar_download_outputs(tsar_ctx *ctx, float *depth_out, float *normals_out, float *confid_out);
 /* Device pointer of a field (for zero-copy consumers such as a fusion stage on the same GPU). */
 int tsar_device_ptr(tsar_ctx *ctx, int field, void **dev_ptr);
 
@@ -199,7 +217,11 @@ int tsar_depthmap_host(tsar_ctx *ctx, int W, int H, int n_images, const float *c
 
 /* ---- gSLICr (north-star item 4) ------------------------------------------------------------------- */
 /* core_engine::Process_Frame + Get_Seg_Res (gSLICr_core_engine.h:11-33; sequence
- * gSLICr_seg_engine.cpp:30-46).  bgrx = img_w*img_h uchar4 (x=B,y=G,z=R as load_image fills it);
+ * gSLICr_seg_engine.cpp:30-46).  bgrx = img_w*img_h uchar4 with the bytes of the reference's UChar4Image: its colour
+ * conversion reads byte 0 as blue, byte 1 as green, byte 2 as red (gSLICr_seg_engine_shared.h:21-23).  Note that the
+ * reference's load_image (main.cpp:190-201) stores OpenCV's B into `.b` = byte 2 and R into `.r` = byte 0, so TSAR runs
+ * the conversion with red and blue exchanged; callers that want the reference's labels fill the bytes as load_image
+ * does (R, G, B, x).  The C++ class itself is exported as well (include/tsar_gslicr_abi.h).
  * labels_out = img_w*img_h int32.  Host pointers. */
 int tsar_slic(tsar_ctx *ctx, const unsigned char *bgrx, const tsar_slic_settings *s, int *labels_out);
 

@@ -59,4 +59,42 @@ if [ -f "$HERE/ref_slic_driver.cu" ] && need "$OUT/libgslic_ref.so" "$HERE/ref_s
   echo "[build_ref] libgslic_ref.so"
   $NVCC $COMMON -I"$REF" -I"$REF/gSLICr_Lib" "$HERE/ref_slic_driver.cu" -o "$OUT/libgslic_ref.so"
 fi
+# 4. the reference's HOST code for rows f1 / f3 (per-region RANSAC, weak-texture detector): line ranges of main.cpp cut into
+#    a temp dir and wrapped by ref_host_driver.cpp (plain g++, no CUDA, no OpenCV: see that file)
+if [ -f "$HERE/ref_host_driver.cpp" ] && need "$OUT/libtsar_ref_host.so" "$HERE/ref_host_driver.cpp" "$REF/main.cpp" "$REF/cameraGeometryUtils.h" "$HERE/build_ref.sh"; then
+  echo "[build_ref] libtsar_ref_host.so"
+  TMP="$(mktemp -d)"
+  trap 'rm -rf "$TMP"' EXIT
+  M="$REF/main.cpp"
+  # every range must start and end on the lines this recipe expects, otherwise fail loudly
+  sed -n '59p' "$M" | grep -q 'const int Robthr = 4;'
+  sed -n '64p' "$M" | grep -q 'const int sizerat = 2.5;'
+  sed -n '147p' "$M" | grep -q '^void calcLinePara('
+  sed -n '164p' "$M" | grep -q '^}'
+  sed -n '214p' "$M" | grep -q '^cv::Mat roberts(cv::Mat srcImage) {'
+  sed -n '242p' "$M" | grep -q '^void Connect(Mat dstImage'
+  sed -n '362p' "$M" | grep -q '^}'
+  sed -n '365p' "$M" | grep -q '^void texture(InputFiles& inputFiles, GlobalState\* gs) {'
+  sed -n '596p' "$M" | grep -q '^}'
+  sed -n '1520p' "$M" | grep -q '^    if (true) {'
+  sed -n '1730p' "$M" | grep -q '^    }'
+  sed -n '1729p' "$M" | grep -q '^        }'
+  sed -n '107p' "$REF/cameraGeometryUtils.h" | grep -q '^float disparityDepthConversion(float f, float baseline, float d) {'
+  sed -n '59,64p' "$M" > "$TMP/ref_slice_constants.inc"
+  sed -n '107,111p' "$REF/cameraGeometryUtils.h" > "$TMP/ref_slice_ddc.inc"
+  sed -n '147,164p' "$M" > "$TMP/ref_slice_calcline.inc"
+  sed -n '214,362p' "$M" > "$TMP/ref_slice_connect.inc"
+  sed -n '365,596p' "$M" > "$TMP/ref_slice_texture.inc"
+  sed -n '1520,1730p' "$M" > "$TMP/ref_slice_ransac.inc"
+  g++ -std=c++14 -O2 -fPIC -shared -w -ffp-contract=off -I"$TMP" "$HERE/ref_host_driver.cpp" -o "$OUT/libtsar_ref_host.so"
+  rm -rf "$TMP"; trap - EXIT
+fi
+# 5. harness that plays the reference's gslic() call site, compiled against the REFERENCE's gSLICr / ORUtils headers and
+#    linked against the drop-in class in libtsar_b200.so (tests/gslicr_harness.cu)
+PKGLIB="$HERE/../tsar-mvs_b200"
+if [ -f "$HERE/../tests/gslicr_harness.cu" ] && [ -f "$PKGLIB/libtsar_b200.so" ] && need "$OUT/libgslicr_harness.so" "$HERE/../tests/gslicr_harness.cu" "$PKGLIB/libtsar_b200.so" "$HERE/build_ref.sh"; then
+  echo "[build_ref] libgslicr_harness.so"
+  $NVCC $COMMON -I"$REF" "$HERE/../tests/gslicr_harness.cu" -o "$OUT/libgslicr_harness.so" -L"$PKGLIB" -ltsar_b200 \
+        -Xlinker -rpath -Xlinker '$ORIGIN/../../tsar-mvs_b200'
+fi
 echo "[build_ref] done: $(ls "$OUT")"

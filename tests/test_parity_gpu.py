@@ -223,6 +223,33 @@ def test_glue_and_depth_completion_bit_exact(env, small):
     mine.close(); ref.close()
 
 
+def test_reliable_flags_and_output_payloads(env, small):
+    """lines->scale from APD's weak.png (main.cpp:1499-1514: white, green and red pixels are reliable) and from the
+    confidence map; tsar_download_outputs hands out exactly the payloads of TSAR_disp.dmb / TSAR_normals.dmb."""
+    pkg, rb = env
+    L = pkg._lib
+    params, mine, _ = pc.make_engines(pkg, small, iterations=2, variants=())
+    H, W = small["H"], small["W"]
+    rng = np.random.RandomState(3)
+    bgr = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    kinds = np.array([[255, 255, 255], [0, 255, 0], [0, 0, 255], [255, 0, 0], [0, 255, 255], [254, 255, 255], [0, 0, 0]], np.uint8)
+    pick = rng.randint(0, len(kinds) + 3, (H, W))
+    for k, col in enumerate(kinds):
+        bgr[pick == k] = col
+    want = ((bgr == [255, 255, 255]).all(-1) | (bgr == [0, 255, 0]).all(-1) | (bgr == [0, 0, 255]).all(-1)).astype(np.float32)
+    assert 0.2 < want.mean() < 0.5
+    mine.scale_from_weak_png(bgr)
+    assert np.array_equal(mine.download(L.F_SCALE), want)
+    mine.depthmap(SEED)
+    out4, confid = mine.download(L.F_NORM4), mine.download(L.F_CONFID)
+    mine.scale_from_confidence(0.8)
+    assert np.array_equal(mine.download(L.F_SCALE), (confid > 0.8).astype(np.float32))
+    depth, normals, cf = mine.download_outputs()
+    assert pc.frac_bit_exact(depth, out4[..., 3]) == 1.0 and pc.frac_bit_exact(normals, np.ascontiguousarray(out4[..., :3])) == 1.0
+    assert pc.frac_bit_exact(cf, confid) == 1.0
+    mine.close()
+
+
 def test_edge_cases(env):
     """Odd sizes (last row outside the reference's checkerboard grid), V = 1 and V = 2, tiny images."""
     pkg, rb = env
@@ -369,6 +396,40 @@ def test_slic_labels_bit_exact(env, cfg, size, enforce):
     assert (mine == ref).all(), f"{(mine != ref).mean():.4%} of labels differ"
     assert len(np.unique(mine)) > 4
     assert (full >= 0).all() and full.max() < (bgrx.shape[0] // size) * (bgrx.shape[1] // size)
+
+
+def test_gslicr_core_engine_drop_in(env, tmp_path):
+    """gSLICr::engines::core_engine exported by libtsar_b200.so under the reference's mangled names, driven by a harness
+    compiled against the REFERENCE's own gSLICr / ORUtils headers that plays gslic() (main.cpp:598-660): labels equal the
+    reference's GPU engine, Draw_Segmentation_Result marks label boundaries, Write_Seg_Res_To_PGM writes the 16-bit map."""
+    import ctypes as C
+    pkg, rb = env
+    so = os.path.join(pc.ROOT, "oracle", "_ref", "libgslicr_harness.so")
+    assert os.path.exists(so), "oracle/_ref/libgslicr_harness.so missing: run `make oracle` where the reference checkout exists"
+    h = C.CDLL(so)
+    scene = pkg.scene.make_scene("C1", with_colour=True)
+    rgbx = pkg.scene.box_downsample4(scene["bgr"])
+    hh, ww = rgbx.shape[:2]
+    labels = np.zeros((hh, ww), np.int32)
+    drawn = np.zeros((hh, ww, 4), np.uint8)
+    pgm = str(tmp_path / "seg.pgm")
+    rc = h.gslicr_harness_run(rgbx.ctypes.data_as(C.c_void_p), ww, hh, 20, 5, C.c_float(5.0), 0, labels.ctypes.data_as(C.c_void_p),
+                              drawn.ctypes.data_as(C.c_void_p), pgm.encode())
+    assert rc == 0
+    ref, _ = rb.ref_slic(rgbx, spixel_size=20, no_iters=5, coh_weight=5.0, enforce_connectivity=False)
+    assert (labels == ref).all(), f"{(labels != ref).mean():.4%} of labels differ"
+    inner = np.zeros((hh, ww), bool)
+    inner[1:-1, 1:-1] = True
+    edge = np.zeros((hh, ww), bool)
+    edge[1:-1, 1:-1] = ((labels[1:-1, 1:-1] != labels[1:-1, 2:]) | (labels[1:-1, 1:-1] != labels[1:-1, :-2]) |
+                        (labels[1:-1, 1:-1] != labels[:-2, 1:-1]) | (labels[1:-1, 1:-1] != labels[2:, 1:-1]))
+    assert (drawn[edge] == np.array([0, 0, 255, 0], np.uint8)).all()
+    assert (drawn[inner & ~edge] == rgbx[inner & ~edge]).all()
+    assert (drawn[~inner] == 7).all()                       # border pixels are not written (GPU.cu:229)
+    raw = open(pgm, "rb").read()
+    head = f"P5\n{ww} {hh}\n65535\n".encode()
+    assert raw.startswith(head) and len(raw) == len(head) + 2 * ww * hh
+    assert np.array_equal(np.frombuffer(raw[len(head):], ">u2").reshape(hh, ww), labels.astype(np.uint16))
 
 
 def test_reference_entry_points_drop_in(env, small):
@@ -533,14 +594,18 @@ def test_wmf_cooperative_equals_per_thread(env, monkeypatch):
     assert 0.05 < outs["0"][3].mean() < 0.999
 
 
-def test_region_plane_fit_matches_restatement(env, small):
-    """Per-region RANSAC plane fit (main.cpp:1520-1730) -- the reference's host program cannot be built here (OpenCV,
-    Windows), so the checker is the scalar C restatement (oracle/oracle_cpu.c) fed with the same random stream;
-    both sides are IEEE double without contraction: bit-exact bar.  Also checks the fit is geometrically right."""
+def test_region_plane_fit_matches_reference_code(env, small):
+    """Per-region RANSAC plane fit on the device (one cooperative kernel, loop termination on the device) against the
+    reference's OWN loop -- main.cpp:1520-1730 cut out of the checkout and compiled by oracle/build_ref.sh
+    (oracle/_ref/libtsar_ref_host.so) -- fed with the same rand() stream; both sides are IEEE double without contraction:
+    bit-exact bar.  Also: the C restatement agrees, the fit is geometrically right, the seeded device stream reproduces,
+    and a second call on the same context (persistent scratch) gives the same planes."""
     pkg, rb = env
     L = pkg._lib
     from oracle import cpu_binding as cb
+    from oracle import ref_host_binding as rh
     from tsar_mvs_b200.engine import cameras_to_struct
+    assert rh.available(), "oracle/_ref/libtsar_ref_host.so missing: run `make oracle` where the reference checkout exists"
     scene = small
     params, mine, _ = pc.make_engines(pkg, scene, variants=())
     H, W = scene["H"], scene["W"]
@@ -559,18 +624,37 @@ def test_region_plane_fit_matches_restatement(env, small):
     mine.upload(L.F_DEPTH, disp); mine.upload(L.F_SCALE, scale); mine.upload(L.F_CANNY, scene["canny"])
     p0 = np.tile(np.array([0, 0, 1, -1], np.float32), (len(text), 1))
     fitted = mine.fit_region_planes(text, size, rnd, p0)
+    again = mine.fit_region_planes(text, size, rnd, p0)
+    assert pc.frac_bit_exact(fitted, again) == 1.0
+    stream = np.concatenate([rnd[r] for r in range(len(text)) if text[r] == -1])
+    ref, used = rh.fit_regions(scene["cams"][0], scene["cam_f"], disp, scale, scene["canny"], text, size, stream, p0)
+    assert used == len(stream)
+    assert pc.frac_bit_exact(fitted, ref) == 1.0, (fitted, ref)
     cams = cameras_to_struct(scene["cams"])
     for r in range(len(text)):
         if text[r] != -1:
             assert np.array_equal(fitted[r], p0[r])
             continue
-        want, used = cb.fit_region_plane(pkg._lib.TsarCamera, cams[0], scene["cam_f"], disp, scale, scene["canny"], r, size[r], rnd[r], p0[r])
-        assert used > 1000
+        want, n_used = cb.fit_region_plane(pkg._lib.TsarCamera, cams[0], scene["cam_f"], disp, scale, scene["canny"], r, size[r], rnd[r], p0[r])
+        assert n_used > 1000
         assert pc.frac_bit_exact(fitted[r], want) == 1.0, (r, fitted[r], want)
         # the fitted plane is the facet's true plane (n.X + d = 0 in the reference frame), up to sign
         true = scene["region_norm4"][r].astype(np.float64)   # generator planes carry a small perturbation
         cosang = abs(np.dot(fitted[r][:3], true[:3]) / np.linalg.norm(fitted[r][:3]) / np.linalg.norm(true[:3]))
         assert cosang > np.cos(np.radians(8.0)), (r, fitted[r], true)
+    # device-generated stream (tsar_fit_region_planes_seeded) == the reference's loop fed with that stream
+    seeded = mine.fit_region_planes(text, size, None, p0, seed=77)
+    with np.errstate(over="ignore"):
+        stream = np.concatenate([mine.ransac_rand_stream(77, r) for r in range(len(text)) if text[r] == -1])
+    ref2, _ = rh.fit_regions(scene["cams"][0], scene["cam_f"], disp, scale, scene["canny"], text, size, stream, p0)
+    assert pc.frac_bit_exact(seeded, ref2) == 1.0, (seeded, ref2)
+    assert mine.lib.tsar_ransac_rand_value(77, 4, 5) == int(stream[per + 5])
+    # edge cases: a region without any reliable pixel keeps its plane; a one-region table
+    scale0 = scale.copy()
+    scale0[scene["labels"] == 1] = 0
+    mine.upload(L.F_SCALE, scale0)
+    kept = mine.fit_region_planes(text, size, rnd, p0)
+    assert np.array_equal(kept[1], p0[1]) and pc.frac_bit_exact(kept[4], fitted[4]) == 1.0
     mine.close()
 
 
@@ -677,7 +761,7 @@ def test_c2_agreement_with_reference_as_written(env):
 
 def test_full_size_properties(env, monkeypatch):
     """Size-independent properties at BASELINE config C2 (3100x2050, 10 source views): determinism, 8-bit vs fp32 source
-    textures identical, duplicate-candidate skipping on/off identical, evaluation count."""
+    textures identical, evaluation count."""
     import torch
     pkg, rb = env
     L = pkg._lib
@@ -706,8 +790,6 @@ def test_full_size_properties(env, monkeypatch):
     assert pc.frac_bit_exact(a, b) == 1.0                                   # deterministic
     c, _ = run((("TSAR_B200_NO_U8", "1"),))
     assert pc.frac_bit_exact(a, c) == 1.0                                   # 8-bit textures == fp32 textures
-    d, _ = run((("TSAR_B200_NO_DEDUP", "1"),))
-    assert pc.frac_bit_exact(a, d) == 1.0                                   # duplicate skipping changes nothing
     gt = pc.gt_agreement(a, scene)
     assert gt["frac_within_1pct_textured"] > 0.95, gt                       # converged to the true surface
     assert 6.6e9 < n_ev < 6.8e9                                             # 6.67 G pmCost evaluations per depthmap as written
@@ -822,6 +904,26 @@ def test_cli_full_tsar_flow_with_detector(env, tmp_path):
     assert np.median(err_fill) < 0.01
     ground = (labels == 0) & (without > 0)
     assert np.mean(with_fill[ground] == without[ground]) > 0.95   # textured regions are left as PatchMatch found them
+    # -all_views runs the same whole flow (detector, gSLICr, PatchMatch, RANSAC, completion) for every view: view 0 must
+    # give the same files as the one-view command, bit for bit -- without and with the weighted-median stages (-wmf)
+    for extra in ([], ["-wmf"]):
+        r1 = subprocess.run([sys.executable, os.path.join(pc.ROOT, "tsar_cli.py")] + names + ["-images_folder", root + "images/"] + common + extra,
+                            capture_output=True, text=True, cwd=pc.ROOT)
+        assert r1.returncode == 0, r1.stderr[-2000:]
+        one = {f: open(os.path.join(root, "APD", "00000000", f), "rb").read() for f in ("TSAR_disp.dmb", "TSAR_normals.dmb", "TSAR_confidence.dmb")}
+        for f in one:
+            os.remove(os.path.join(root, "APD", "00000000", f))
+        r3 = subprocess.run([sys.executable, os.path.join(pc.ROOT, "tsar_cli.py"), "-all_views", "-images_folder", root + "images/"] + common + extra,
+                            capture_output=True, text=True, cwd=pc.ROOT)
+        assert r3.returncode == 0, r3.stderr[-2000:]
+        assert f"{len(names)} of {len(names)} reference views" in r3.stdout
+        for f, want in one.items():
+            assert open(os.path.join(root, "APD", "00000000", f), "rb").read() == want, (extra, f)
+        if not extra:
+            assert one["TSAR_disp.dmb"][16:] == with_fill.tobytes()      # and the completion really ran in both
+        else:
+            wmf_depth = dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_disp.dmb"))
+            assert (wmf_depth != with_fill).mean() > 1e-4               # the weighted-median fill changed pixels
 
 
 def test_plain_c_program_runs_a_depthmap(env, tmp_path):

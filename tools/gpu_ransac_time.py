@@ -55,6 +55,35 @@ want, used = cb.fit_region_plane(pkg._lib.TsarCamera, cams[0], scene["cam_f"], d
 res["cpu_ms_1_region"] = (time.perf_counter() - t0) * 1e3
 res["cpu_points"] = int(used)
 res["bit_exact_vs_cpu"] = bool(np.array_equal(fitted[r], want))
+mine.close()
+
+# ---- a C2 view with the weak-texture detector's REAL region table (thousands of regions, a few of them weak) ----------
+import torch  # noqa: E402
+from tsar_mvs_b200 import texture as tx  # noqa: E402
+sc2 = pkg.scene.make_scene("C2", backend="torch", device="cuda:0")
+imgs = [im.contiguous() for im in sc2["images"]]
+ref_u8 = imgs[0].cpu().numpy().astype(np.uint8)
+t0 = time.perf_counter()
+det = tx.detect(ref_u8)
+res["c2_detector_host_ms"] = (time.perf_counter() - t0) * 1e3
+res["c2_regions"] = int(len(det["text"]))
+res["c2_weak_regions"] = int((det["text"] == -1).sum())
+eng = pkg.DepthmapEngine(0)
+eng.set_views_device([t.data_ptr() for t in imgs], sc2["W"], sc2["H"], cameras_to_struct(sc2["cams"]), sc2["subset"], cam_f=sc2["cam_f"])
+eng.set_params(pkg.make_params(box=11, iterations=8, min_disparity=sc2["min_disparity"], max_disparity=sc2["max_disparity"]))
+eng.set_labels_quarter(det["labels_q"])
+eng.init_planes(1); eng.iterate(8, 1); eng.lrdiff(); eng.getview()
+confid = eng.download(L.F_CONFID)
+eng.upload(L.F_SCALE, (confid > 0.8).astype(np.float32))
+p0 = np.tile(np.array([0, 0, 1, -1], np.float32), (len(det["text"]), 1))
+eng.fit_region_planes(det["text"], det["size"], None, p0, seed=5)       # warm-up (allocates the persistent scratch)
+n0 = eng.launch_count()
+t0 = time.perf_counter()
+planes = eng.fit_region_planes(det["text"], det["size"], None, p0, seed=5)
+res["c2_fit_ms_all_weak_regions_seeded_stream"] = (time.perf_counter() - t0) * 1e3
+res["c2_fit_kernel_launches"] = int(eng.launch_count() - n0)
+lab_full = tx.expand_labels(det["labels_q"], sc2["W"], sc2["H"])
+res["c2_weak_region_reliable_points"] = [int(((lab_full == r) & (confid > 0.8)).sum()) for r in np.nonzero(det["text"] == -1)[0]]
+eng.close()
 print(json.dumps(res))
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "ransac_time.json"), "w"), indent=1)
-mine.close()

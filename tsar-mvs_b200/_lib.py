@@ -50,9 +50,9 @@ EXPORTS = [
     "tsar_create", "tsar_destroy", "tsar_last_error", "tsar_sync", "tsar_set_views", "tsar_set_params",
     "tsar_init_planes", "tsar_load_planes", "tsar_launch", "tsar_iterate", "tsar_eval_planes", "tsar_lrdiff",
     "tsar_getview", "tsar_get_disp", "tsar_update_scale_2", "tsar_update_scale", "tsar_compute_disp", "tsar_wmf",
-    "tsar_wmf_final", "tsar_set_regions", "tsar_fit_region_planes", "tsar_ransac_rand_per_region", "tsar_upload", "tsar_download", "tsar_device_ptr", "tsar_depthmap",
+    "tsar_wmf_final", "tsar_set_regions", "tsar_fit_region_planes", "tsar_fit_region_planes_seeded", "tsar_ransac_rand_value", "tsar_ransac_rand_per_region", "tsar_upload", "tsar_download", "tsar_device_ptr", "tsar_depthmap",
     "tsar_depthmap_host", "tsar_slic", "tsar_launch_count", "tsar_eval_count", "tsar_version", "tsar_dbg_tex_sample", "tsar_dbg_peaks", "tsar_dbg_eval_rounding", "tsar_dbg_candidate_stats", "tsar_dbg_tex_formats", "tsar_profile", "tsar_profile_read",
-    "tsar_weak_edges", "tsar_weak_connect", "tsar_weak_boundary", "tsar_weak_close_border", "tsar_weak_regions", "tsar_set_labels_quarter",
+    "tsar_weak_edges", "tsar_weak_connect", "tsar_weak_boundary", "tsar_weak_close_border", "tsar_weak_regions", "tsar_set_labels_quarter", "tsar_scale_from_weak_png", "tsar_scale_from_confidence", "tsar_download_outputs",
 ]
 
 
@@ -92,6 +92,8 @@ def load():
         "tsar_wmf": (i, [vp, i]), "tsar_wmf_final": (i, [vp, i]),
         "tsar_set_regions": (i, [vp, i, vp, vp]),
         "tsar_fit_region_planes": (i, [vp, i, vp, vp, vp, vp]),
+        "tsar_fit_region_planes_seeded": (i, [vp, i, vp, vp, u64, vp]),
+        "tsar_ransac_rand_value": (C.c_uint32, [u64, i, i]),
         "tsar_ransac_rand_per_region": (i, []),
         "tsar_upload": (i, [vp, i, vp, C.c_size_t]),
         "tsar_download": (i, [vp, i, vp, C.c_size_t]),
@@ -116,6 +118,9 @@ def load():
         "tsar_weak_close_border": (i, [vp, i, i]),
         "tsar_weak_regions": (i, [vp, i, i, vp, i, i, i, vp, vp, vp, vp]),
         "tsar_set_labels_quarter": (i, [vp, vp, i, i]),
+        "tsar_scale_from_weak_png": (i, [vp, vp]),
+        "tsar_scale_from_confidence": (i, [vp, C.c_float]),
+        "tsar_download_outputs": (i, [vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

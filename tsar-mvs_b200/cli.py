@@ -39,17 +39,18 @@ from .engine import DepthmapEngine, make_params
 
 NUMERIC = {"blocksize", "iterations", "n_best", "cost_gamma", "depth_min", "depth_max", "max_views", "min_angle", "max_angle",
            "cam_scale", "cost_tau_color", "cost_tau_gradient", "cost_alpha", "disp_tol", "normal_tol", "census_epsilon",
-           "self_similarity_n", "good_factor", "num_img_processed", "seed", "synthetic", "device"}
+           "self_similarity_n", "good_factor", "num_img_processed", "seed", "synthetic", "device", "lanes", "io_threads"}
 PATHS = {"images_folder", "mslp_folder", "krt_file", "output_folder", "p_folder", "camera_folder", "calib_file", "pmvs_folder",
          "bounding_folder", "regions_file", "regions_text", "regions_size"}
-BOOLS = {"color_processing", "view_selection", "import_apd", "no_display", "all_views", "no_weak_texture", "write_ply"}
+BOOLS = {"color_processing", "view_selection", "import_apd", "no_display", "all_views", "no_weak_texture", "write_ply", "wmf", "no_slic", "no_write"}
 
 
 def parse_args(argv):
     """getParametersFromCommandLine (main.cpp:708-1009), tolerant in the same places."""
     opt = dict(images=[], blocksize=19, iterations=8, n_best=2, cost_comb=1, cam_scale=1.0, depth_min=-1.0, depth_max=-1.0,
                seed=20240601, device=0, images_folder="", mslp_folder="", output_folder="", synthetic=None,
-               color_processing=False, import_apd=False, all_views=False, no_weak_texture=False, write_ply=False, regions_file=None, regions_text=None, regions_size=None)
+               color_processing=False, import_apd=False, all_views=False, no_weak_texture=False, write_ply=False, wmf=False, no_slic=False, no_write=False,
+               regions_file=None, regions_text=None, regions_size=None, lanes=2, io_threads=4)
     i = 0
     while i < len(argv):
         a = argv[i]
@@ -153,17 +154,123 @@ def write_synthetic_dataset(cfg_name, root):
     return sc, names
 
 
+def write_rig_dataset(cfg_name, root, backend="numpy", device=None, png_compression=1):
+    """A multi-view synthetic dataset (scene.make_rig: C3 = 38 cameras on two arcs, C4seq = 300-frame sequence) in the
+    reference's folder layout; pair.txt lists every camera's 10 nearest neighbours.  Returns the image names."""
+    import cv2
+    cfg = scene.CONFIGS[cfg_name]
+    K, Rs, Cs, neighbours = scene.make_rig(cfg)
+    os.makedirs(os.path.join(root, "images"), exist_ok=True)
+    os.makedirs(os.path.join(root, "cams"), exist_ok=True)
+    names = []
+    for i, img in scene.render_rig(cfg, backend=backend, device=device):
+        name = f"{i:08d}.png"
+        cv2.imwrite(os.path.join(root, "images", name), img, [cv2.IMWRITE_PNG_COMPRESSION, int(png_compression)])
+        R, C = Rs[i], Cs[i]
+        write_cam_txt(os.path.join(root, "cams", f"{i:08d}_cam.txt"), K, R, -R @ C, 0.7 * cfg["radius"], 1.45 * cfg["radius"])
+        names.append(name)
+    write_pair_txt(os.path.join(root, "pair.txt"), neighbours)
+    return names
+
+
+# ---- one reference view: the TSAR flow of runGipuma (main.cpp:1268-1866) -----------------------------------------
+def _load_image_bytes(bgr_quarter):
+    """UChar4Image as load_image fills it (main.cpp:190-201): OpenCV's B goes to `.b` (byte 2), G to byte 1, R to `.r`
+    (byte 0)."""
+    h, w = bgr_quarter.shape[:2]
+    out = np.zeros((h, w, 4), np.uint8)
+    out[..., 0], out[..., 1], out[..., 2] = bgr_quarter[..., 2], bgr_quarter[..., 1], bgr_quarter[..., 0]
+    return out
+
+
+def quarter_colour(bgr_full):
+    """main.cpp:619-622: two pyrDown with explicit halved sizes on the colour image."""
+    import cv2
+    c2 = cv2.pyrDown(bgr_full, dstsize=(bgr_full.shape[1] // 2, bgr_full.shape[0] // 2))
+    return cv2.pyrDown(c2, dstsize=(c2.shape[1] // 2, c2.shape[0] // 2))
+
+
+def run_view(eng, opt, view, outputs=None):
+    """The whole per-view flow on a context whose views and parameters are already set: texture() -> gslic() -> firstcuda
+    -> [weak.png] -> sliccuda -> per-region RANSAC -> fakecuda -> fillcuda (main.cpp:1893-1896, 1459-1783).
+    view: dict(gray_u8 = reference image (H x W uint8) for the detector, bgr = colour reference image or None, apd_dir,
+    seed).  outputs: optional (depth, normals, confid) host buffers (arrays or raw addresses).  Returns
+    (depth, normals, confid, info)."""
+    from . import _lib as L
+    info = {}
+    H, W = eng.H, eng.W
+    text = size = None
+    if opt["regions_file"]:
+        labels = np.load(opt["regions_file"]).astype(np.float32)
+        text = np.load(opt["regions_text"]).astype(np.float32)
+        size = np.load(opt["regions_size"]).astype(np.float32) if opt["regions_size"] else \
+            np.array([(labels == r).sum() / 16.0 for r in range(len(text))], np.float32)
+        eng.upload(L.F_CANNY, labels)
+    elif not opt["no_weak_texture"]:            # texture() runs first in the reference's main (main.cpp:1893)
+        from . import texture
+        det = texture.detect(view["gray_u8"])
+        info["regions"], info["weak_regions"] = len(det["text"]) - 1, int((det["text"] == -1).sum())
+        text, size = det["text"], det["size"]
+        eng.set_labels_quarter(det["labels_q"])
+    if view.get("bgr") is not None and not opt["no_slic"] and min(H, W) >= 4 * 20:   # gslic() (main.cpp:598-660): superpixels of
+        info["slic_labels"] = eng.slic(_load_image_bytes(quarter_colour(view["bgr"])))  # size 20 on the quarter-size image; debug output only
+    if opt["import_apd"]:                       # shipped flow, main.cpp:1459-1490
+        f = float(np.float32(view["cam_f"]))
+        depth = dmb.read_dmb(os.path.join(view["apd_dir"], "depths_geom.dmb"))
+        normal = dmb.read_dmb(os.path.join(view["apd_dir"], "normals.dmb"))
+        eng.upload(L.F_NORM4, np.concatenate([normal, np.zeros((H, W, 1), np.float32)], axis=-1))
+        eng.upload(L.F_COST, np.ones((H, W), np.float32))
+        eng.upload(L.F_DEPTH, (np.float32(f) / depth).astype(np.float32))
+        eng.get_disp()
+    else:                                       # the block the reference has commented out (gipuma.cu:1741-1758)
+        eng.init_planes(int(view["seed"]))
+        eng.iterate(opt["iterations"], int(view["seed"]))
+        eng.lrdiff()
+    eng.getview()
+    n_weak = int((text == -1).sum()) if text is not None else 0
+    if text is not None and (n_weak or opt["wmf"]):
+        weak_png = os.path.join(view["apd_dir"], "weak.png")
+        if opt["import_apd"] and os.path.exists(weak_png):     # reliable pixels: main.cpp:1499-1514
+            import cv2
+            eng.scale_from_weak_png(cv2.imread(weak_png, cv2.IMREAD_COLOR))
+        else:
+            if opt["import_apd"]:
+                print(f"[tsar_cli] {weak_png} not found: reliable pixels taken from the confidence map", file=sys.stderr)
+            eng.scale_from_confidence(0.8)      # stands in for APD's weak.png
+        if opt["wmf"]:                          # gipuma_WMF x 4 (gipuma.cu:1809-1812)
+            for it in range(4):
+                eng.wmf(it)
+        planes = np.tile(np.array([0, 0, 1, -1], np.float32), (len(text), 1))
+        if n_weak:                              # main.cpp:1520-1730
+            planes = eng.fit_region_planes(text, size, None, planes, seed=int(view["seed"]))
+        eng.set_regions(text, planes)
+        if n_weak:
+            eng.update_scale_2()                # fakecuda
+            eng.update_scale()                  # fillcuda
+        if opt["wmf"]:                          # gipuma_WMF_Final x 6 (gipuma.cu:1844-1847)
+            for it in range(6):
+                eng.wmf_final(it)
+    eng.compute_disp()
+    bufs = outputs if outputs is not None else (None, None, None)
+    depth, normals, confid = eng.download_outputs(*bufs)
+    return depth, normals, confid, info
+
+
 # ---- the driver ---------------------------------------------------------------------------------------------
 def run(argv):
     opt = parse_args(argv)
     mslp = opt["mslp_folder"]
     if opt["synthetic"]:
         mslp = mslp or "./synthetic_" + opt["synthetic"] + "/"
-        _, names = write_synthetic_dataset(opt["synthetic"], mslp)
+        if "rig" in scene.CONFIGS.get(opt["synthetic"], {}):
+            names = write_rig_dataset(opt["synthetic"], mslp)
+        else:
+            _, names = write_synthetic_dataset(opt["synthetic"], mslp)
         opt["images"] = opt["images"] or names
         opt["images_folder"] = os.path.join(mslp, "images/")
     if opt["all_views"]:
-        return run_all_views(opt, mslp)
+        run_all_views(opt, mslp)
+        return 0
     if not opt["images"]:
         print(__doc__)
         return 2
@@ -192,52 +299,23 @@ def run(argv):
     eng = DepthmapEngine(int(opt["device"]))
     eng.set_views(images, cams, subset, cam_f=f)
     eng.set_params(params)
-    from . import _lib as L
     out_dir = os.path.join(mslp, "APD", stem)
     H, W = images[0].shape
-    if opt["import_apd"]:                       # shipped flow, main.cpp:1459-1490
-        depth = dmb.read_dmb(os.path.join(out_dir, "depths_geom.dmb"))
-        normal = dmb.read_dmb(os.path.join(out_dir, "normals.dmb"))
-        n4 = np.concatenate([normal, np.zeros((H, W, 1), np.float32)], axis=-1)
-        eng.upload(L.F_NORM4, n4)
-        eng.upload(L.F_COST, np.ones((H, W), np.float32))
-        eng.upload(L.F_DEPTH, (np.float32(f) / depth).astype(np.float32))
-        eng.get_disp()
-    else:
-        eng.init_planes(int(opt["seed"]))
-        eng.iterate(opt["iterations"], int(opt["seed"]))
-        eng.lrdiff()
-    eng.getview()
-    confid = eng.download(L.F_CONFID)
-    text = size = None
-    if opt["regions_file"]:
-        labels = np.load(opt["regions_file"]).astype(np.float32)
-        text = np.load(opt["regions_text"]).astype(np.float32)
-        size = np.load(opt["regions_size"]).astype(np.float32) if opt["regions_size"] else \
-            np.array([(labels == r).sum() / 16.0 for r in range(len(text))], np.float32)
-        eng.upload(L.F_CANNY, labels)
-    elif not opt["no_weak_texture"]:            # texture() runs first in the reference's main (main.cpp:1896)
-        from . import texture
-        det = texture.detect(images[0].astype(np.uint8))
-        n_weak = int((det["text"] == -1).sum())
-        print(f"[tsar_cli] weak-texture detector: {len(det['text']) - 1} regions, {n_weak} weakly textured")
-        if n_weak:
-            text, size = det["text"], det["size"]
-            eng.set_labels_quarter(det["labels_q"])
-    if text is not None:
-        eng.upload(L.F_SCALE, (confid > 0.8).astype(np.float32))       # reliable pixels (stands in for APD's weak.png)
-        rng = np.random.RandomState(int(opt["seed"]) & 0x7fffffff)
-        rnd = rng.randint(0, 2 ** 31 - 1, size=(len(text), eng.lib.tsar_ransac_rand_per_region())).astype(np.uint32)
-        planes = eng.fit_region_planes(text, size, rnd, np.tile(np.array([0, 0, 1, -1], np.float32), (len(text), 1)))
-        eng.set_regions(text, planes)
-        eng.update_scale_2()
-        eng.update_scale()
-    eng.compute_disp()
-    out = eng.download(L.F_NORM4)
-    dmb.write_outputs(out_dir, out)
+    bgr = None
+    if not opt["no_slic"] and not names[0].endswith(".npy"):
+        import cv2
+        bgr = cv2.imread(os.path.join(opt["images_folder"], names[0]), cv2.IMREAD_COLOR)
+    view = dict(gray_u8=_imread_gray(os.path.join(opt["images_folder"], names[0])).astype(np.uint8) if opt["color_processing"] else images[0].astype(np.uint8),
+                bgr=bgr, apd_dir=out_dir, seed=int(opt["seed"]), cam_f=f)
+    depth, normals, confid, info = run_view(eng, opt, view)
+    if "regions" in info:
+        print(f"[tsar_cli] weak-texture detector: {info['regions']} regions, {info['weak_regions']} weakly textured")
+    os.makedirs(out_dir, exist_ok=True)
+    dmb.write_dmb(os.path.join(out_dir, "TSAR_disp.dmb"), depth)
+    dmb.write_dmb(os.path.join(out_dir, "TSAR_normals.dmb"), normals)
     dmb.write_dmb(os.path.join(out_dir, "TSAR_confidence.dmb"), confid)   # computed but never written by the reference
     if opt["write_ply"]:                        # main.cpp:1836-1843 (always on there; 27 B per pixel, so opt-in here)
-        dmb.write_model_ply(os.path.join(out_dir, "TSAR_model.ply"), out[..., 3], out[..., :3], images[0], Ks[0], Rs[0], ts[0])
+        dmb.write_model_ply(os.path.join(out_dir, "TSAR_model.ply"), depth, normals, images[0], Ks[0], Rs[0], ts[0])
     print(f"[tsar_cli] {stem}: {W}x{H}, {len(subset)} source views -> {out_dir}/TSAR_disp.dmb, TSAR_normals.dmb")
     eng.close()
     return 0
@@ -250,14 +328,35 @@ def read_pair_neighbours(path, camera_id):
     return [int(line[1 + 2 * j]) for j in range(int(line[0]))]
 
 
-def run_all_views(opt, mslp):
-    """Persistent multi-view driver (SURVEY section 8 rows e/f4): see the module docstring."""
+def read_pair_table(path):
+    """pair.txt parsed once: {camera id: [neighbour camera ids in file order]} (main.cpp:1351-1376)."""
+    lines = open(path).read().split("\n")
+    n = int(lines[0].split()[0])
+    table = {}
+    for k in range(n):
+        cam = int(lines[2 * k + 1].split()[0])
+        tok = lines[2 * k + 2].split()
+        table[cam] = [int(tok[1 + 2 * j]) for j in range(int(tok[0]))]
+    return table
+
+
+def run_all_views(opt, mslp, quiet=False):
+    """Persistent multi-view driver (SURVEY section 8 rows e/f4), the replacement of the per-view process loop of
+    scripts/pipes.sh:30-49.  Every reference view of this rank runs the whole TSAR flow (run_view).  Host side:
+      * a decoder pool reads the images this rank needs (its views + their pair.txt neighbours) in parallel, while the
+        first views already run; decoded images go to HBM once and stay there;
+      * `lanes` contexts (own stream, own host thread) take views from a shared queue, so a view's host stages (cameras,
+        weak-texture detector, file hand-over) overlap the kernels of the other lane;
+      * results arrive in pinned buffers that already carry the .dmb header and are written by a writer pool.
+    Returns a dict with the throughput and where the time went."""
     import concurrent.futures as cf
+    import itertools
+    import threading
     import time
 
     import torch
 
-    from . import _lib as L
+    from .engine import cameras_to_struct
     from .shard import views_for_rank
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     ndev = torch.cuda.device_count()
@@ -268,22 +367,86 @@ def run_all_views(opt, mslp):
     names = opt["images"] or sorted(n for n in os.listdir(folder) if n.lower().endswith((".jpg", ".jpeg", ".png", ".npy")))
     ids = [int(n[4:8]) for n in names]                          # camera id of each image (main.cpp:1347-1349)
     by_id = {c: k for k, c in enumerate(ids)}
-    krt = [read_cam_txt(os.path.join(mslp, "cams", f"{n[:8]}_cam.txt")) for n in names]
     t0 = time.perf_counter()
-    pool = [torch.from_numpy(_imread_gray(os.path.join(folder, n), opt["color_processing"])).to(f"cuda:{dev}") for n in names]   # resident, once
-    H, W = pool[0].shape
+    krt = [read_cam_txt(os.path.join(mslp, "cams", f"{n[:8]}_cam.txt")) for n in names]
+    pairs = read_pair_table(os.path.join(mslp, "pair.txt"))
     mine = views_for_rank(len(names), rank, world)
+    neigh = {r: [by_id[c] for c in pairs.get(ids[r], []) if c in by_id] for r in mine}
+    needed = sorted(set(mine) | {i for r in mine for i in neigh[r]})
+    want_colour = not opt["no_slic"]
+    stats = dict(decode_s=0.0, detect_s=0.0, gpu_wait_s=0.0, write_s=0.0, setup_s=0.0)
+    stats_lock = threading.Lock()
+
+    def add(key, dt):
+        with stats_lock:
+            stats[key] += dt
+
+    # ---- decoder pool: grey image of every needed view (+ colour for this rank's reference views) ------------------
+    def decode(i):
+        t = time.perf_counter()
+        path = os.path.join(folder, names[i])
+        grey = _imread_gray(path, opt["color_processing"])
+        u8 = grey.astype(np.uint8) if not opt["color_processing"] else _imread_gray(path).astype(np.uint8)
+        bgr = None
+        if want_colour and i in mine_set and not path.endswith(".npy"):
+            import cv2
+            bgr = cv2.imread(path, cv2.IMREAD_COLOR)
+        add("decode_s", time.perf_counter() - t)
+        return grey, u8, bgr
+
+    mine_set = set(mine)
+    io_pool = cf.ThreadPoolExecutor(max(1, int(opt["io_threads"])))
+    order = list(itertools.chain.from_iterable([r] + neigh[r] for r in mine))   # decode in the order the lanes ask
+    seen, decode_order = set(), []
+    for i in order:
+        if i not in seen:
+            seen.add(i); decode_order.append(i)
+    fut = {i: io_pool.submit(decode, i) for i in decode_order}
+    resident, resident_lock = {}, {i: threading.Lock() for i in needed}
+
+    def device_image(i):
+        with resident_lock[i]:
+            if i not in resident:
+                grey = fut[i].result()[0]
+                resident[i] = torch.from_numpy(np.ascontiguousarray(grey, np.float32)).to(f"cuda:{dev}")   # resident, once
+            return resident[i]
+
+    H, W = fut[decode_order[0]].result()[0].shape
+    npx = W * H
+
+    def out_buffers():
+        """pinned buffers holding header + payload of the three output files of one view"""
+        bufs = []
+        for nb in (1, 3, 1):
+            t = torch.empty(16 + npx * nb * 4, dtype=torch.uint8).pin_memory()
+            t.numpy()[:16].view(np.int32)[:] = [1, H, W, nb]            # fileIoUtils.h:333-381
+            bufs.append(t)
+        return bufs
+
+    n_lanes = max(1, min(int(opt["lanes"]), len(mine)))
     lanes = []
-    for _ in range(min(2, max(1, len(mine)))):
+    for _ in range(n_lanes):
         st = torch.cuda.Stream(device=dev)
-        lanes.append(dict(eng=DepthmapEngine(dev, stream=st.cuda_stream), stream=st))
-    done = []
+        free = __import__("queue").Queue()
+        for _k in range(2):                                            # two sets: one being written while the next view runs
+            free.put(out_buffers())
+        lanes.append(dict(eng=DepthmapEngine(dev, stream=st.cuda_stream), stream=st, free=free))
+    add("setup_s", time.perf_counter() - t0)
+    done, writes, infos = [], [], {}
+
+    def write_view(out_dir, bufs, free):
+        t = time.perf_counter()
+        os.makedirs(out_dir, exist_ok=True)
+        for name, b in zip(("TSAR_disp.dmb", "TSAR_normals.dmb", "TSAR_confidence.dmb"), bufs):
+            with open(os.path.join(out_dir, name), "wb", buffering=0) as f:
+                f.write(memoryview(b.numpy()))
+        free.put(bufs)
+        add("write_s", time.perf_counter() - t)
 
     def process(k, lane):
         eng = lane["eng"]
         r = mine[k]
-        nb = [by_id[c] for c in read_pair_neighbours(os.path.join(mslp, "pair.txt"), ids[r]) if c in by_id]
-        sel = [r] + nb
+        sel = [r] + neigh[r]
         Ks = []
         for i in sel:
             K = krt[i][0].copy()
@@ -295,21 +458,23 @@ def run_all_views(opt, mslp):
         f = float(np.float32(cams[0]["f"]))
         params = make_params(box=opt["blocksize"], iterations=opt["iterations"], n_best=opt["n_best"], cost_comb=opt["cost_comb"],
                              min_disparity=float(np.float32(f / np.float32(dmax))), max_disparity=float(np.float32(f / np.float32(dmin))))
-        from .engine import cameras_to_struct
-        eng.set_views_device([pool[i].data_ptr() for i in sel], W, H, cameras_to_struct(cams), list(range(1, len(sel))), cam_f=f)
+        eng.set_views_device([device_image(i).data_ptr() for i in sel], W, H, cameras_to_struct(cams), list(range(1, len(sel))), cam_f=f)
         eng.set_params(params)
-        eng.init_planes(int(opt["seed"]) + r)
-        eng.iterate(opt["iterations"], int(opt["seed"]) + r)
-        eng.lrdiff(); eng.getview(); eng.compute_disp()
-        out, confid = eng.download(L.F_NORM4), eng.download(L.F_CONFID)
+        _, u8, bgr = fut[r].result()
         out_dir = os.path.join(mslp, "APD", names[r][:8])
-        dmb.write_outputs(out_dir, out)
-        dmb.write_dmb(os.path.join(out_dir, "TSAR_confidence.dmb"), confid)
+        bufs = lane["free"].get()                                      # blocks while both sets are still being written
+        view = dict(gray_u8=u8, bgr=bgr, apd_dir=out_dir, seed=int(opt["seed"]) + r, cam_f=f)
+        t = time.perf_counter()
+        _, _, _, info = run_view(eng, opt, view, outputs=tuple(b.data_ptr() + 16 for b in bufs))
+        add("gpu_wait_s", time.perf_counter() - t)
+        infos[r] = {k_: v for k_, v in info.items() if k_ != "slic_labels"}
+        if opt["no_write"]:
+            lane["free"].put(bufs)
+        else:
+            writes.append(io_pool.submit(write_view, out_dir, bufs, lane["free"]))
         done.append(r)
         return r
 
-    import itertools
-    import threading
     ticket, ticket_lock = itertools.count(), threading.Lock()
 
     def lane_worker(j):     # one host thread per lane (a context is never shared); views are taken from a shared queue,
@@ -323,13 +488,25 @@ def run_all_views(opt, mslp):
     with cf.ThreadPoolExecutor(len(lanes)) as ex:
         for fu in [ex.submit(lane_worker, j) for j in range(len(lanes))]:
             fu.result()
+    for w in writes:
+        w.result()
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
+    launches = sum(lane["eng"].launch_count() for lane in lanes)
     for lane in lanes:
         lane["eng"].close()
-    print(f"[tsar_cli] rank {rank}/{world}: {len(done)} of {len(names)} reference views ({W}x{H}) in {dt:.2f} s "
-          f"({len(done) / dt:.2f} depthmaps/s incl. decoding and .dmb writing) -> {os.path.join(mslp, 'APD')}")
-    return 0
+    io_pool.shutdown()
+    res = dict(rank=rank, world=world, views=len(done), images=len(names), W=W, H=H, seconds=dt, depthmaps_per_s=len(done) / dt,
+               lanes=n_lanes, io_threads=int(opt["io_threads"]), gpu_launches=int(launches),
+               host_seconds={k: round(v, 3) for k, v in stats.items()},
+               bytes_decoded=int(sum(os.path.getsize(os.path.join(folder, names[i])) for i in needed)),
+               bytes_written=0 if opt["no_write"] else int(len(done) * (48 + 20 * npx)),
+               weak_regions=int(sum(v.get("weak_regions", 0) for v in infos.values())))
+    if not quiet:
+        print(f"[tsar_cli] rank {rank}/{world}: {len(done)} of {len(names)} reference views ({W}x{H}) in {dt:.2f} s "
+              f"({len(done) / dt:.2f} depthmaps/s incl. decoding and .dmb writing) -> {os.path.join(mslp, 'APD')}\n"
+              f"[tsar_cli] host seconds (summed over threads): {res['host_seconds']}")
+    return res
 
 
 if __name__ == "__main__":

@@ -24,6 +24,17 @@
 
 using namespace tsar;
 
+struct RansacScratch {
+    int *block_counts = nullptr, *list = nullptr, *totals = nullptr, *hyp_counts = nullptr, *regions = nullptr;
+    float3 *pts = nullptr;
+    uint32_t *rnd = nullptr;
+    RansacJob *jobs = nullptr;
+    float4 *out = nullptr;
+    RansacState *states = nullptr;
+    size_t px_cap = 0;
+    int nt_cap = 0, grid = 0;
+};
+
 struct tsar_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -82,6 +93,7 @@ struct tsar_ctx {
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // around every checkerboard kernel
     SlicState slic;
+    RansacScratch ransac;
 };
 
 #define CK(call)                                                                                    \
@@ -364,6 +376,8 @@ int tsar_destroy(tsar_ctx *ctx) {
     cudaFree(ctx->d_tex); cudaFree(ctx->d_cams); cudaFree(ctx->rng); cudaFree(ctx->rng_batch); cudaFree(ctx->scratch);
     cudaFree(ctx->region_text); cudaFree(ctx->region_plane); cudaFree(ctx->d_flag); cudaFree(ctx->stage32);
     slic_free(ctx->slic);
+    { RansacScratch &r = ctx->ransac; cudaFree(r.block_counts); cudaFree(r.list); cudaFree(r.totals); cudaFree(r.hyp_counts); cudaFree(r.regions);
+      cudaFree(r.pts); cudaFree(r.rnd); cudaFree(r.jobs); cudaFree(r.out); cudaFree(r.states); }
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -768,96 +782,166 @@ int tsar_set_labels_quarter(tsar_ctx *ctx, const int *labels, int wq, int hq) {
     return TSAR_OK;
 }
 
-int tsar_fit_region_planes(tsar_ctx *ctx, int n_regions, const float *region_text, const float *region_size,
-                           const uint32_t *rnd, float *region_norm4) {
+// Persistent device scratch of the region fit (grow-only: cudaMalloc / cudaFree synchronise the whole device and would
+// stall the other pipelined context).
+static int ensure_ransac(tsar_ctx *ctx, size_t n_px, int nt) {
+    RansacScratch &r = ctx->ransac;
+    const size_t nb = (n_px + 1023) / 1024;
+    if (n_px > r.px_cap) {
+        cudaFree(r.block_counts); cudaFree(r.list);
+        r.block_counts = nullptr; r.list = nullptr; r.px_cap = 0;
+        CK(cudaMalloc(&r.block_counts, nb * sizeof(int)));
+        CK(cudaMalloc(&r.list, n_px * sizeof(int)));
+        r.px_cap = n_px;
+    }
+    if (nt > r.nt_cap) {
+        cudaFree(r.totals); cudaFree(r.pts); cudaFree(r.rnd); cudaFree(r.jobs); cudaFree(r.out); cudaFree(r.states);
+        cudaFree(r.hyp_counts); cudaFree(r.regions);
+        r.totals = nullptr; r.pts = nullptr; r.rnd = nullptr; r.jobs = nullptr; r.out = nullptr; r.states = nullptr;
+        r.hyp_counts = nullptr; r.regions = nullptr; r.nt_cap = 0;
+        const int cap = std::max(nt, 4);
+        CK(cudaMalloc(&r.totals, (size_t)cap * sizeof(int)));
+        CK(cudaMalloc(&r.pts, (size_t)cap * kRansacKeepAll * sizeof(float3)));
+        CK(cudaMalloc(&r.rnd, (size_t)cap * kRansacRandPerRegion * sizeof(uint32_t)));
+        CK(cudaMalloc(&r.jobs, (size_t)cap * sizeof(RansacJob)));
+        CK(cudaMalloc(&r.out, (size_t)cap * sizeof(float4)));
+        CK(cudaMalloc(&r.states, (size_t)cap * sizeof(RansacState)));
+        CK(cudaMalloc(&r.hyp_counts, (size_t)cap * kRansacBatch * sizeof(int)));
+        CK(cudaMalloc(&r.regions, (size_t)cap * sizeof(int)));
+        CK(cudaMemsetAsync(r.hyp_counts, 0, (size_t)cap * kRansacBatch * sizeof(int), ctx->stream));  // the kernel leaves it zeroed
+        r.nt_cap = cap;
+    }
+    if (r.grid == 0) {
+        int sms = 148, per_sm = 0;
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ransac_fit_kernel, kRansacSlice, 0));
+        if (per_sm < 1) FAIL(TSAR_ERR_CUDA, "region-fit kernel does not fit on an SM");
+        r.grid = sms * std::min(per_sm, 2);   // all CTAs must be co-resident (grid-wide barriers)
+    }
+    return TSAR_OK;
+}
+
+// rnd != nullptr: region-major host array, kRansacRandPerRegion values for EVERY region; else the device stream of `seed`
+static int fit_region_planes(tsar_ctx *ctx, int n_regions, const float *region_text, const float *region_size,
+                             const uint32_t *rnd, unsigned long long seed, float *region_norm4) {
     int rc = need_ready(ctx);
     if (rc) return rc;
-    if (n_regions < 1 || !region_text || !region_size || !rnd || !region_norm4) FAIL(TSAR_ERR_ARG, "bad region arguments");
+    if (n_regions < 1 || !region_text || !region_size || !region_norm4) FAIL(TSAR_ERR_ARG, "bad region arguments");
     std::vector<int> targets;
     for (int r = 0; r < n_regions; r++)
         if (region_text[r] == -1.0f) targets.push_back(r);
     if (targets.empty()) return TSAR_OK;
-    const int n = ctx->W * ctx->H, nb = (n + 1023) / 1024, nt = (int)targets.size();
-    int *d_counts = nullptr, *d_list = nullptr, *d_total = nullptr;
-    float3 *d_pts = nullptr;
-    uint32_t *d_rnd = nullptr;
-    RansacJob *d_jobs = nullptr;
-    float4 *d_out = nullptr;
-    RansacState *d_state = nullptr;
-    int *d_hyp_counts = nullptr, *d_cursors = nullptr;
+    const size_t n = (size_t)ctx->W * ctx->H;
+    if (n > 0x7fffffffull) FAIL(TSAR_ERR_ARG, "image too large for 32-bit pixel indices");
+    const int nb = (int)((n + 1023) / 1024), nt = (int)targets.size();
+    if ((rc = ensure_ransac(ctx, n, nt))) return rc;
+    RansacScratch &S = ctx->ransac;
+    cudaStream_t st = ctx->stream;
     std::vector<RansacJob> jobs(nt);
-    auto cleanup = [&]() {
-        cudaFree(d_counts); cudaFree(d_list); cudaFree(d_total); cudaFree(d_pts); cudaFree(d_rnd); cudaFree(d_jobs); cudaFree(d_out);
-        cudaFree(d_state); cudaFree(d_hyp_counts); cudaFree(d_cursors);
-    };
-#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); ctx->err = std::string(#call ": ") + cudaGetErrorString(e_); return TSAR_ERR_CUDA; } } while (0)
-    CKF(cudaMalloc(&d_counts, (size_t)nb * 4)); CKF(cudaMalloc(&d_list, (size_t)n * 4)); CKF(cudaMalloc(&d_total, 4));
-    CKF(cudaMalloc(&d_pts, (size_t)nt * kRansacMaxPts * sizeof(float3)));
-    CKF(cudaMalloc(&d_rnd, (size_t)nt * kRansacRandPerRegion * 4));
-    CKF(cudaMalloc(&d_jobs, (size_t)nt * sizeof(RansacJob))); CKF(cudaMalloc(&d_out, (size_t)nt * sizeof(float4)));
-    CKF(cudaMalloc(&d_state, (size_t)nt * sizeof(RansacState))); CKF(cudaMalloc(&d_cursors, (size_t)nt * 4));
-    CKF(cudaMalloc(&d_hyp_counts, (size_t)nt * kRansacBatch * 4));
-    CKF(cudaMemsetAsync(d_hyp_counts, 0, (size_t)nt * kRansacBatch * 4, ctx->stream));
+    std::vector<float4> out(nt);
     for (int t = 0; t < nt; t++) {
         const int r = targets[t];
-        ransac_flag_kernel<<<nb, 1024, 0, ctx->stream>>>(ctx->scale, ctx->canny, n, r, d_counts);
-        ransac_scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(d_counts, nb, d_total);
-        ransac_scatter_kernel<<<nb, 1024, 0, ctx->stream>>>(ctx->scale, ctx->canny, n, r, d_counts, d_list);
-        int total = 0;
-        CKF(cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CKF(cudaStreamSynchronize(ctx->stream));
-        const int used = std::min(total, kRansacMaxPts);
-        float3 *pts = d_pts + (size_t)t * kRansacMaxPts;
-        if (used > 0) ransac_points_kernel<<<(used + 255) / 256, 256, 0, ctx->stream>>>(ctx->glue, ctx->depth, d_list, total, used, pts);
-        ctx->launches += 4;
-        jobs[t].pts = pts; jobs[t].n = used; jobs[t].size = region_size[r];
-        jobs[t].rnd = d_rnd + (size_t)t * kRansacRandPerRegion; jobs[t].out = d_out + t;
-        CKF(cudaMemcpyAsync(d_rnd + (size_t)t * kRansacRandPerRegion, rnd + (size_t)r * kRansacRandPerRegion,
-                            (size_t)kRansacRandPerRegion * 4, cudaMemcpyHostToDevice, ctx->stream));
+        jobs[t].pts = S.pts + (size_t)t * kRansacKeepAll;
+        jobs[t].n = 0;
+        jobs[t].size = region_size[r];
+        jobs[t].rnd = S.rnd + (size_t)t * kRansacRandPerRegion;
+        jobs[t].out = S.out + t;
+        out[t] = make_float4(region_norm4[4 * r], region_norm4[4 * r + 1], region_norm4[4 * r + 2], region_norm4[4 * r + 3]);
     }
-    std::vector<float4> out(nt);
-    for (int t = 0; t < nt; t++) out[t] = make_float4(region_norm4[4 * targets[t]], region_norm4[4 * targets[t] + 1], region_norm4[4 * targets[t] + 2], region_norm4[4 * targets[t] + 3]);
-    CKF(cudaMemcpyAsync(d_out, out.data(), (size_t)nt * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    CKF(cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)nt * sizeof(RansacJob), cudaMemcpyHostToDevice, ctx->stream));
-    int max_n = 0;
-    for (int t = 0; t < nt; t++) max_n = std::max(max_n, jobs[t].n);
-    if (max_n > 0) {
-        const dim3 cgrid((max_n + 255) / 256, nt);
-        ransac_state_init_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(d_jobs, d_state, nt);
+    // (pageable host sources: cudaMemcpyAsync returns once they are staged, so the vectors may go out of scope)
+    CK(cudaMemcpyAsync(S.jobs, jobs.data(), (size_t)nt * sizeof(RansacJob), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S.out, out.data(), (size_t)nt * sizeof(float4), cudaMemcpyHostToDevice, st));
+    if (rnd) {
+        for (int t = 0; t < nt; t++)
+            CK(cudaMemcpyAsync(S.rnd + (size_t)t * kRansacRandPerRegion, rnd + (size_t)targets[t] * kRansacRandPerRegion,
+                               (size_t)kRansacRandPerRegion * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    } else {
+        CK(cudaMemcpyAsync(S.regions, targets.data(), (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, st));
+        ransac_rand_kernel<<<dim3((kRansacRandPerRegion + 255) / 256, nt), 256, 0, st>>>(S.rnd, S.regions, nt, kRansacRandPerRegion, seed);
         ctx->launches++;
-        // RANSAC hypotheses: the inlier threshold is constant between hypotheses 1000 j and 1000 (j+1)
-        for (int first = 0; first < kRansacIters;) {
-            const int count = first == 0 ? 1 : std::min(kRansacBatch, kRansacIters - first);
-            ransac_batch_count_kernel<<<cgrid, 256, 0, ctx->stream>>>(d_jobs, d_state, 0, first, count, d_hyp_counts);
-            ransac_select_kernel<<<nt, 1024, 0, ctx->stream>>>(d_jobs, d_state, 0, first, count, d_hyp_counts, d_cursors);
-            ctx->launches += 2;
-            first += count;
-        }
-        CKF(cudaGetLastError());
-        // local refinement: every trial perturbs the CURRENT best, so trials are evaluated speculatively in batches
-        // and the first accepted one is committed; the host only reads the cursors back
-        std::vector<int> cursors(nt, 0);
-        const int spec = 256;
-        for (int guard = 0; guard <= kRefineTotal; guard++) {
-            ransac_batch_count_kernel<<<cgrid, 256, 0, ctx->stream>>>(d_jobs, d_state, 1, 0, spec, d_hyp_counts);
-            ransac_select_kernel<<<nt, 1024, 0, ctx->stream>>>(d_jobs, d_state, 1, 0, spec, d_hyp_counts, d_cursors);
-            ctx->launches += 2;
-            CKF(cudaMemcpyAsync(cursors.data(), d_cursors, (size_t)nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CKF(cudaStreamSynchronize(ctx->stream));
-            bool done = true;
-            for (int t = 0; t < nt; t++) done = done && cursors[t] >= kRefineTotal;
-            if (done) break;
-        }
-        CKF(cudaGetLastError());
     }
-    CKF(cudaMemcpyAsync(out.data(), d_out, (size_t)nt * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
-    CKF(cudaStreamSynchronize(ctx->stream));
-#undef CKF
+    // stable compaction of every target region's reliable pixels (raster order, as the reference collects them) and their
+    // back-projection; list lengths stay on the device
+    for (int t = 0; t < nt; t++) {
+        const int r = targets[t];
+        ransac_flag_kernel<<<nb, 1024, 0, st>>>(ctx->scale, ctx->canny, (int)n, r, S.block_counts);
+        ransac_scan_blocks_kernel<<<1, 1024, 0, st>>>(S.block_counts, nb, S.totals + t);
+        ransac_scatter_kernel<<<nb, 1024, 0, st>>>(ctx->scale, ctx->canny, (int)n, r, S.block_counts, S.list);
+        ransac_points_kernel<<<(kRansacKeepAll + 255) / 256, 256, 0, st>>>(ctx->glue, ctx->depth, S.list, S.totals + t,
+                                                                         S.pts + (size_t)t * kRansacKeepAll, S.jobs + t);
+        ctx->launches += 4;
+    }
+    CK(cudaGetLastError());
+    // the whole fit: one cooperative launch, loop termination on the device
+    RansacFitArgs fa;
+    fa.jobs = S.jobs; fa.states = S.states; fa.counts = S.hyp_counts; fa.n_jobs = nt;
+    void *kargs[] = {&fa};
+    CK(cudaLaunchCooperativeKernel((const void *)ransac_fit_kernel, dim3(S.grid), dim3(kRansacSlice), kargs, 0, st));
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out.data(), S.out, (size_t)nt * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));   // the only host wait: the result
     for (int t = 0; t < nt; t++) {
         float *o = region_norm4 + 4 * targets[t];
         o[0] = out[t].x; o[1] = out[t].y; o[2] = out[t].z; o[3] = out[t].w;
     }
-    cleanup();
+    return TSAR_OK;
+}
+
+int tsar_fit_region_planes(tsar_ctx *ctx, int n_regions, const float *region_text, const float *region_size,
+                           const uint32_t *rnd, float *region_norm4) {
+    if (!ctx) return TSAR_ERR_ARG;
+    if (!rnd) FAIL(TSAR_ERR_ARG, "rnd is null (use tsar_fit_region_planes_seeded for a device-generated stream)");
+    return fit_region_planes(ctx, n_regions, region_text, region_size, rnd, 0ull, region_norm4);
+}
+
+int tsar_fit_region_planes_seeded(tsar_ctx *ctx, int n_regions, const float *region_text, const float *region_size,
+                                  uint64_t seed, float *region_norm4) {
+    if (!ctx) return TSAR_ERR_ARG;
+    return fit_region_planes(ctx, n_regions, region_text, region_size, nullptr, (unsigned long long)seed, region_norm4);
+}
+
+uint32_t tsar_ransac_rand_value(uint64_t seed, int region, int index) { return ransac_rand_value((unsigned long long)seed, region, index); }
+
+int tsar_scale_from_confidence(tsar_ctx *ctx, float threshold) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    const size_t n = (size_t)ctx->W * ctx->H;
+    scale_from_confidence_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->confid, threshold, ctx->scale, n);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TSAR_OK;
+}
+
+int tsar_scale_from_weak_png(tsar_ctx *ctx, const unsigned char *bgr) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (!bgr) FAIL(TSAR_ERR_ARG, "weak.png pixels are null");
+    const size_t n = (size_t)ctx->W * ctx->H;
+    if ((rc = ensure_scratch(ctx, n * 3))) return rc;
+    CK(cudaMemcpyAsync(ctx->scratch, bgr, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+    scale_from_weak_png_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uchar3 *)ctx->scratch, ctx->scale, n);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));  // the caller's buffer may go away
+    return TSAR_OK;
+}
+
+int tsar_download_outputs(tsar_ctx *ctx, float *depth_out, float *normals_out, float *confid_out) {
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if ((rc = consolidate(ctx))) return rc;
+    const size_t n = (size_t)ctx->W * ctx->H;
+    if (depth_out || normals_out) {
+        if ((rc = ensure_scratch(ctx, n * 16))) return rc;
+        float *d = (float *)ctx->scratch, *nr = d + n;
+        split_outputs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->plane[0], d, nr, n);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        if (depth_out) CK(cudaMemcpyAsync(depth_out, d, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (normals_out) CK(cudaMemcpyAsync(normals_out, nr, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (confid_out) CK(cudaMemcpyAsync(confid_out, ctx->confid, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return TSAR_OK;
 }
 

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/tsar_b200.h"
@@ -29,8 +30,50 @@ struct ShimCtx {
     tsar_ctx *ctx = nullptr;
     bool views = false;
     int n_regions = 0;
+    unsigned long long fingerprint = 0;   // of everything ensure_views mirrors (sizes, view subset, image arrays, parameters)
 };
 std::map<const void *, ShimCtx> g_ctx;
+std::mutex g_ctx_mutex;   // the map only: one GlobalState is driven by one host thread, as in the reference
+
+ShimCtx &ctx_of(const void *gs) {
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    return g_ctx[gs];   // std::map nodes are stable: the reference stays valid while other keys are inserted
+}
+
+// TSAR_B200_WMF=1 re-enables the weighted-median stages at the launch sites where the reference has them commented out:
+// gipuma_WMF x 4 after gipuma_getview in sliccuda (gipuma.cu:1809-1812), gipuma_WMF_Final x 6 after gipuma_update_scale in
+// fillcuda (gipuma.cu:1844-1847)
+bool wmf_enabled() {
+    const char *e = getenv("TSAR_B200_WMF");
+    return e && e[0] == '1';
+}
+
+unsigned long long mix(unsigned long long h, unsigned long long v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    return h;
+}
+
+// cheap fingerprint of what a mirrored context depends on: a host loop that re-uses one GlobalState for another reference
+// view (new images in cuArray, another subset, other parameters) gets a fresh mirror instead of stale views
+unsigned long long fingerprint_of(const AbiState &gs) {
+    const tsar_abi::CameraParameters_cu &cp = *gs.cameras;
+    const tsar_abi::AlgorithmParameters &ap = *gs.params;
+    unsigned long long h = 1469598103934665603ull;
+    h = mix(h, (unsigned long long)cp.cols); h = mix(h, (unsigned long long)cp.rows); h = mix(h, (unsigned long long)cp.viewSelectionSubsetNumber);
+    h = mix(h, (unsigned long long)(size_t)gs.cuArray[0]);
+    for (int i = 0; i < cp.viewSelectionSubsetNumber; i++) {
+        const int id = cp.viewSelectionSubset[i];
+        h = mix(h, (unsigned long long)id);
+        if (id >= 0 && id < tsar_abi::kMaxImages) h = mix(h, (unsigned long long)(size_t)gs.cuArray[id]);
+    }
+    unsigned int bits;
+    memcpy(&bits, &ap.min_disparity, 4); h = mix(h, bits);
+    memcpy(&bits, &ap.max_disparity, 4); h = mix(h, bits);
+    memcpy(&bits, &cp.f, 4); h = mix(h, bits);
+    h = mix(h, (unsigned long long)ap.box_hsize * 131 + ap.box_vsize); h = mix(h, (unsigned long long)ap.iterations);
+    h = mix(h, (unsigned long long)ap.n_best * 7 + ap.cost_comb); h = mix(h, ap.color_processing ? 1ull : 0ull);
+    return h;
+}
 
 int fail(tsar_ctx *ctx, const char *what, int rc) {
     fprintf(stderr, "[tsar_b200 shim] %s failed (%d): %s\n", what, rc, ctx ? tsar_last_error(ctx) : "no context");
@@ -47,8 +90,10 @@ int ensure_views(AbiState &gs, ShimCtx &s) {
         int rc = tsar_create(dev, nullptr, &s.ctx);
         if (rc) return fail(nullptr, "tsar_create", rc);
     }
-    if (s.views) return 0;
-    cudaDeviceSynchronize();
+    cudaDeviceSynchronize();   // the caller fills managed memory on the host between the calls
+    const unsigned long long fp = fingerprint_of(gs);
+    if (s.views && fp == s.fingerprint) return 0;
+    s.views = false;
     const tsar_abi::CameraParameters_cu &cp = *gs.cameras;
     const int W = cp.cols, H = cp.rows, V = cp.viewSelectionSubsetNumber;
     int n_images = 1;
@@ -86,6 +131,7 @@ int ensure_views(AbiState &gs, ShimCtx &s) {
         if (!ok) {
             fprintf(stderr, "[tsar_b200 shim] reading view %d from its cudaArray failed: %s\n", i, cudaGetErrorString(cudaGetLastError()));
             cudaFree(rgba);
+            for (float *p : dev_imgs) cudaFree(p);
             return TSAR_ERR_CUDA;
         }
     }
@@ -101,6 +147,7 @@ int ensure_views(AbiState &gs, ShimCtx &s) {
     p.color_processing = ap.color_processing ? 1 : 0;
     if ((rc = tsar_set_params(s.ctx, &p))) return fail(s.ctx, "tsar_set_params", rc);
     s.views = true;
+    s.fingerprint = fp;
     return 0;
 }
 
@@ -128,7 +175,7 @@ int ensure_regions(AbiState &gs, ShimCtx &s, size_t n) {
 
 int firstcuda(GlobalState &gs_) {
     tsar_abi::GlobalState &gs = reinterpret_cast<tsar_abi::GlobalState &>(gs_);
-    ShimCtx &s = g_ctx[&gs];
+    ShimCtx &s = ctx_of(&gs);
     int rc = ensure_views(gs, s);
     if (rc) return rc;
     const size_t n = (size_t)gs.cameras->cols * gs.cameras->rows;
@@ -155,7 +202,7 @@ int firstcuda(GlobalState &gs_) {
 
 int sliccuda(GlobalState &gs_) {
     tsar_abi::GlobalState &gs = reinterpret_cast<tsar_abi::GlobalState &>(gs_);
-    ShimCtx &s = g_ctx[&gs];
+    ShimCtx &s = ctx_of(&gs);
     int rc = ensure_views(gs, s);
     if (rc) return rc;
     const size_t n = (size_t)gs.cameras->cols * gs.cameras->rows;
@@ -164,13 +211,19 @@ int sliccuda(GlobalState &gs_) {
     if ((rc = up(s, TSAR_F_COST, gs.lines->c, n * 4))) return rc;
     if ((rc = up(s, TSAR_F_LRDIFF, gs.lines->lrdiff, n * 4))) return rc;
     if ((rc = tsar_getview(s.ctx))) return fail(s.ctx, "tsar_getview", rc);
+    if (wmf_enabled()) {   // gipuma.cu:1809-1812: reads the reliable flags the caller took from weak.png (main.cpp:1499-1514)
+        if ((rc = up(s, TSAR_F_SCALE, gs.lines->scale, n * 4))) return rc;
+        for (int iter = 0; iter < 4; iter++)
+            if ((rc = tsar_wmf(s.ctx, iter))) return fail(s.ctx, "tsar_wmf", rc);
+        if ((rc = down(s, TSAR_F_SCALE, gs.lines->scale, n * 4))) return rc;
+    }
     if ((rc = down(s, TSAR_F_CONFID, gs.lines->confid, n * 4))) return rc;
     return down(s, TSAR_F_DEPTH, gs.lines->depth, n * 4);
 }
 
 int fakecuda(GlobalState &gs_) {
     tsar_abi::GlobalState &gs = reinterpret_cast<tsar_abi::GlobalState &>(gs_);
-    ShimCtx &s = g_ctx[&gs];
+    ShimCtx &s = ctx_of(&gs);
     int rc = ensure_views(gs, s);
     if (rc) return rc;
     const size_t n = (size_t)gs.cameras->cols * gs.cameras->rows;
@@ -183,7 +236,7 @@ int fakecuda(GlobalState &gs_) {
 
 int fillcuda(GlobalState &gs_) {
     tsar_abi::GlobalState &gs = reinterpret_cast<tsar_abi::GlobalState &>(gs_);
-    ShimCtx &s = g_ctx[&gs];
+    ShimCtx &s = ctx_of(&gs);
     int rc = ensure_views(gs, s);
     if (rc) return rc;
     const size_t n = (size_t)gs.cameras->cols * gs.cameras->rows;
@@ -194,6 +247,9 @@ int fillcuda(GlobalState &gs_) {
     if ((rc = up(s, TSAR_F_SCALE, gs.lines->scale, n * 4))) return rc;
     if ((rc = up(s, TSAR_F_DEPTH, gs.lines->depth, n * 4))) return rc;
     if ((rc = tsar_update_scale(s.ctx))) return fail(s.ctx, "tsar_update_scale", rc);
+    if (wmf_enabled())     // gipuma.cu:1844-1847
+        for (int iter = 0; iter < 6; iter++)
+            if ((rc = tsar_wmf_final(s.ctx, iter))) return fail(s.ctx, "tsar_wmf_final", rc);
     if ((rc = down(s, TSAR_F_SCALE, gs.lines->scale, n * 4))) return rc;
     if ((rc = down(s, TSAR_F_DEPTH, gs.lines->depth, n * 4))) return rc;
     if ((rc = tsar_compute_disp(s.ctx))) return fail(s.ctx, "tsar_compute_disp", rc);
@@ -201,8 +257,11 @@ int fillcuda(GlobalState &gs_) {
     return down(s, TSAR_F_NORM4, gs.lines->norm4, n * 16);
 }
 
-// release the context mirrored for a GlobalState (the reference leaks gs.cs instead, gipuma.cu:1775, Q17)
+// Releases the context mirrored for a GlobalState (the reference leaks gs.cs instead, gipuma.cu:1775, Q17).  Call it before
+// the GlobalState is deleted: contexts are keyed by its address, and a later GlobalState allocated at the same address is
+// only recognised as a different one by its fingerprint (sizes, view subset, image arrays, parameters).
 extern "C" int tsar_shim_release(const void *gs) {
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
     auto it = g_ctx.find(gs);
     if (it == g_ctx.end()) return TSAR_OK;
     tsar_destroy(it->second.ctx);

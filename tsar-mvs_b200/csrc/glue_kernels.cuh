@@ -243,4 +243,31 @@ __global__ void labels_quarter_kernel(const int *__restrict__ lab, int wq, int h
     canny[(size_t)y * W + x] = (float)lab[(size_t)sy * wq + sx];
 }
 
+// lines->scale from the confidence map: 1 where confid > thr.  The shipped flow takes the reliable flags from APD's weak.png
+// (main.cpp:1499-1514); when PatchMatch runs inside the library there is no such file and the confidence of
+// gipuma_getview stands in for it (tsar_scale_from_confidence).
+__global__ void scale_from_confidence_kernel(const float *__restrict__ confid, float thr, float *__restrict__ scale, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) scale[i] = confid[i] > thr ? 1.0f : 0.0f;
+}
+
+// lines->scale from APD's weak.png (main.cpp:1499-1514): 1 where the BGR pixel is white, green (0,255,0) or red (0,0,255);
+// other pixels keep their value (the array is zero after LineState::resize)
+__global__ void scale_from_weak_png_kernel(const uchar3 *__restrict__ bgr, float *__restrict__ scale, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uchar3 p = bgr[i];
+    if ((p.x == 255 && p.y == 255 && p.z == 255) || (p.x == 0 && p.y == 255 && p.z == 0) || (p.x == 0 && p.y == 0 && p.z == 255)) scale[i] = 1.0f;
+}
+
+// Output files hold the depth and the normals in separate arrays (TSAR_disp.dmb: w of the output layout, TSAR_normals.dmb:
+// xyz, main.cpp:1785-1795): split on the device so that the host receives exactly the file payloads.
+__global__ void split_outputs_kernel(const float4 *__restrict__ out4, float *__restrict__ depth, float *__restrict__ normals, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = out4[i];
+    depth[i] = v.w;
+    normals[3 * i] = v.x; normals[3 * i + 1] = v.y; normals[3 * i + 2] = v.z;
+}
+
 }  // namespace tsar

@@ -15,6 +15,7 @@
 // Deviation: when a region has more than 49 999 reliable pixels the reference keeps a random subset
 // (std::shuffle with a clock seed); we keep an evenly strided subset.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,7 +23,8 @@
 
 namespace tsar {
 
-constexpr int kRansacMaxPts = 49999;       // main.cpp:1541-1549: lists are cut to fewer than 50 000 points
+constexpr int kRansacKeepAll = 50000;      // main.cpp:1541: lists of up to 50 000 points are used whole ...
+constexpr int kRansacCut = 49999;          // main.cpp:1547-1549: ... longer ones are cut to 49 999
 constexpr int kRansacIters = 10000;        // main.cpp:1603
 constexpr int kRefineRounds = 1000;        // main.cpp:1662
 constexpr int kRansacRandPerRegion = 3 * kRansacIters + 4 * 4 * kRefineRounds;
@@ -85,10 +87,24 @@ __global__ void ransac_scatter_kernel(const float *__restrict__ scale, const flo
     if (f) list[block_offsets[blockIdx.x] + warp_off[warp] + __popc(b & ((1u << lane) - 1))] = i;
 }
 
-// back-projection of the (sub-sampled) list: main.cpp:1574-1598, float arithmetic, no contraction
+struct RansacJob {
+    const float3 *pts;   // region's points
+    int n;               // number of points (0: region skipped, plane left unchanged); written by ransac_points_kernel
+    float size;          // cannylines->size[region]
+    const uint32_t *rnd; // kRansacRandPerRegion values, in the order the reference calls rand()
+    float4 *out;         // cannylines->norm4[region]
+};
+
+// back-projection of the (sub-sampled) list: main.cpp:1574-1598, float arithmetic, no contraction.  The list length stays
+// on the device (*total): the kernel is launched for the largest possible list and records the number of points used in
+// the region's job, so the host never waits for a count.
 __global__ void ransac_points_kernel(const __grid_constant__ GlueConst g, const float *__restrict__ depth,
-                                     const int *__restrict__ list, int n_all, int n_used, float3 *__restrict__ pts) {
+                                     const int *__restrict__ list, const int *__restrict__ total, float3 *__restrict__ pts,
+                                     RansacJob *__restrict__ job) {
+    const int n_all = *total;
+    const int n_used = n_all <= kRansacKeepAll ? n_all : kRansacCut;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) job->n = n_used;
     if (k >= n_used) return;
     const int src = (n_all == n_used) ? k : (int)(((long long)k * n_all) / n_used);
     const int p = list[src];
@@ -100,6 +116,22 @@ __global__ void ransac_points_kernel(const __grid_constant__ GlueConst g, const 
     o.y = fadd(fadd(fmul(g.Minv[3], x), fmul(g.Minv[4], y)), fmul(g.Minv[5], z));
     o.z = fadd(fadd(fmul(g.Minv[6], x), fmul(g.Minv[7], y)), fmul(g.Minv[8], z));
     pts[k] = o;
+}
+
+// The values rand() would return, generated on the device from a seed (tsar_fit_region_planes_seeded): a counter-based
+// stream, value i of region r = top 31 bits of splitmix64(seed ^ (r << 32) ^ i) -- non-negative ints like rand()'s.
+__host__ __device__ __forceinline__ uint32_t ransac_rand_value(unsigned long long seed, int region, int index) {
+    unsigned long long z = seed ^ ((unsigned long long)(uint32_t)region << 32) ^ (unsigned long long)(uint32_t)index;
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 33);
+}
+__global__ void ransac_rand_kernel(uint32_t *__restrict__ rnd, const int *__restrict__ regions, int n_targets, int per_region,
+                                   unsigned long long seed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    if (i < per_region && t < n_targets) rnd[(size_t)t * per_region + i] = ransac_rand_value(seed, regions[t], i);
 }
 
 // ---- the fit: one CTA per region -----------------------------------------------------------------------------
@@ -123,14 +155,6 @@ __device__ __forceinline__ int ransac_count(const float3 *__restrict__ pts, int 
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += smem_counts[w];
     return tot;
 }
-
-struct RansacJob {
-    const float3 *pts;   // region's points
-    int n;               // number of points (0: region skipped, plane left unchanged)
-    float size;          // cannylines->size[region]
-    const uint32_t *rnd; // kRansacRandPerRegion values, in the order the reference calls rand()
-    float4 *out;         // cannylines->norm4[region]
-};
 
 // Running state of one region's fit (the reference's loop-carried variables, main.cpp:1600-1710)
 struct RansacState {
@@ -171,118 +195,173 @@ __device__ __forceinline__ void ransac_perturbed_plane(const RansacJob &job, con
     ra = __ddiv_rn(ra, sq); rb = __ddiv_rn(rb, sq); rc = __ddiv_rn(rc, sq); rd = __ddiv_rn(rd, sq);
 }
 
-__global__ void ransac_state_init_kernel(const RansacJob *__restrict__ jobs, RansacState *__restrict__ st, int n_jobs) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_jobs) return;
-    RansacState s;
-    s.a = 0; s.b = 0; s.c = 1; s.d = -1; s.maximum = 0;
-    s.depth_abs = (float)(0.0003 * (double)sqrtf(jobs[r].size / 20.0f));  // main.cpp:1552-1553
-    s.cursor = 0;
-    st[r] = s;
-}
+// ---- the whole fit of all regions in ONE persistent cooperative kernel ---------------------------------------------------
+// The reference's loop carries only the best-so-far plane, its inlier count and the adaptive threshold (which changes after
+// hypotheses 0, 1000, 2000, ...), so hypotheses are COUNTED in batches by the whole grid -- a CTA keeps 256 points of one
+// region in registers (as doubles) and runs through the batch, whose plane parameters it computes into shared memory
+// (60 flops per hypothesis versus 8 per point x hypothesis) -- and between two batches one CTA per region applies the
+// reference's sequential rules.  The perturbation trials all depend on the current best: they are counted speculatively,
+// kRefineSpec at a time, and the FIRST accepted one is committed, the cursor moves behind it.  Phases are separated by
+// grid-wide barriers; the loop ends on the device when every region's cursor has passed its last trial, so the host
+// launches once and reads the planes back once.
+struct RansacFitArgs {
+    RansacJob *jobs;          // n_jobs entries (n filled in on the device by ransac_points_kernel)
+    RansacState *states;
+    int *counts;              // n_jobs x kRansacBatch, zero on entry and on exit
+    int n_jobs;
+};
+constexpr int kRefineSpec = 256;      // perturbation trials counted per speculative round
+constexpr int kRansacSlice = 256;     // points per counting task = threads per CTA
 
-// Inlier counts of a batch of hypotheses.  grid = (point slices of 256, regions): a CTA keeps ITS 256 points in
-// registers (as doubles) and runs through all hypotheses of the batch, whose plane parameters every CTA computes
-// redundantly into shared memory (cheap: 60 flops per hypothesis versus 8 per point x hypothesis).  So the points
-// are read once per launch, the planes are shared-memory broadcasts, and the work of one region spreads over
-// n/256 CTAs instead of one.  refine = 0: RANSAC hypotheses first .. first+count-1; refine = 1: perturbation trials
-// cursor .. cursor+count-1 of the current best.
-__global__ void __launch_bounds__(256) ransac_batch_count_kernel(const RansacJob *__restrict__ jobs, const RansacState *__restrict__ states,
-                                                                 int refine, int first, int count, int *__restrict__ counts) {
-    __shared__ double pa[kRansacBatch], pb[kRansacBatch], pc[kRansacBatch], pd[kRansacBatch];
-    __shared__ int cnt_s[kRansacBatch];
-    const RansacJob job = jobs[blockIdx.y];
-    const RansacState st = states[blockIdx.y];
-    const int n = job.n;
-    if (n <= 0 || (int)blockIdx.x * 256 >= n) return;
-    if (refine) {
-        first = st.cursor;
-        count = min(count, kRefineTotal - first);
-        if (count <= 0) return;
-    }
-    for (int h = threadIdx.x; h < count; h += 256) {
-        double a, b, c, d;
-        if (refine) ransac_perturbed_plane(job, st, first + h, a, b, c, d);
-        else ransac_triple_plane(job, first + h, a, b, c, d);
-        pa[h] = a; pb[h] = b; pc[h] = c; pd[h] = d;
-        cnt_s[h] = 0;
-    }
-    __syncthreads();
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    const bool valid = i < n;
-    const float3 p = job.pts[valid ? i : 0];
-    const double x = p.x, y = p.y, z = p.z, thr = (double)st.depth_abs;
-    const int lane = threadIdx.x & 31;
-    for (int h = 0; h < count; h++) {
-        const double r = fabs(dadd(dadd(dadd(dmul(x, pa[h]), dmul(y, pb[h])), dmul(z, pc[h])), pd[h]));
-        const unsigned bal = __ballot_sync(0xffffffffu, valid && r < thr);
-        if (lane == 0 && bal) atomicAdd(&cnt_s[h], __popc(bal));
-    }
-    __syncthreads();
-    int *out = counts + (size_t)blockIdx.y * kRansacBatch;
-    for (int h = threadIdx.x; h < count; h += 256)
-        if (cnt_s[h]) atomicAdd(&out[h], cnt_s[h]);
-}
+struct RansacSmem {
+    double pa[kRansacBatch], pb[kRansacBatch], pc[kRansacBatch], pd[kRansacBatch];
+    int cnt[kRansacBatch];
+    int warp_counts[32];
+    RansacState st;
+};
 
-// Sequential part, one CTA per region: walks the batch's counts in hypothesis order with the reference's
-// acceptance rule (>= replaces the best), applies the adaptive inlier threshold after hypotheses 0, 1000, 2000, ...
-// (main.cpp:1645-1663), or -- refinement -- commits the FIRST accepted perturbation and moves the cursor behind it
-// (later trials of the batch were perturbations of the old best and are evaluated again from the new one).
-__global__ void __launch_bounds__(1024) ransac_select_kernel(const RansacJob *__restrict__ jobs, RansacState *__restrict__ states,
-                                                             int refine, int first, int count, int *__restrict__ counts,
-                                                             int *__restrict__ cursors) {
-    __shared__ int smem_counts[32];
-    __shared__ RansacState sst;
-    const RansacJob job = jobs[blockIdx.x];
-    const int n = job.n;
-    int *cnt = counts + (size_t)blockIdx.x * kRansacBatch;
-    if (n <= 0) { if (threadIdx.x == 0) cursors[blockIdx.x] = kRefineTotal; return; }
-    if (threadIdx.x == 0) {
-        RansacState st = states[blockIdx.x];
-        if (!refine) {
-            int best = -1;
-            for (int h = 0; h < count; h++)
-                if ((double)cnt[h] >= st.maximum) { st.maximum = (double)cnt[h]; best = h; }
-            if (best >= 0) ransac_triple_plane(job, first + best, st.a, st.b, st.c, st.d);
-        } else {
-            const int base = st.cursor, m = min(count, kRefineTotal - base);
-            int hit = -1;
-            for (int h = 0; h < m; h++)
-                if ((double)cnt[h] >= st.maximum) { hit = h; break; }
-            if (hit >= 0) {
-                double a, b, c, d;
-                ransac_perturbed_plane(job, st, base + hit, a, b, c, d);
-                st.a = a; st.b = b; st.c = c; st.d = d; st.maximum = (double)cnt[hit];
-                st.cursor = base + hit + 1;
-            } else {
-                st.cursor = base + max(m, 0);
-            }
-            cursors[blockIdx.x] = st.cursor;
+// counting phase: tasks = (region, slice of 256 points), strided over the grid
+__device__ __forceinline__ void ransac_count_phase(const RansacFitArgs &a, RansacSmem &sm, int refine, int first, int count) {
+    int planes_of = -1;   // region whose batch planes are in shared memory
+    int base = 0;
+    for (int t = 0; t < a.n_jobs; t++) {
+        const RansacJob job = a.jobs[t];
+        const int slices = (job.n + kRansacSlice - 1) / kRansacSlice;
+        // first task index of this region that belongs to this CTA
+        int task = (int)blockIdx.x - (base % (int)gridDim.x);
+        if (task < 0) task += gridDim.x;
+        base += slices;
+        if (job.n <= 0) continue;
+        const RansacState st = a.states[t];
+        int f = first, c = count;
+        if (refine) {
+            f = st.cursor;
+            c = min(count, kRefineTotal - f);
+            if (c <= 0) continue;
         }
-        sst = st;
-    }
-    __syncthreads();
-    // the adaptive threshold step follows hypothesis k whenever k % 1000 == 0; batches end exactly there
-    if (!refine && ((first + count - 1) % 1000) == 0) {
-        const double rat = sst.maximum / (double)n;
-        if (rat < 0.3 && (double)sst.depth_abs < 0.003) {
-            __syncthreads();
-            if (threadIdx.x == 0) sst.depth_abs = (float)((double)sst.depth_abs + 0.0001);
-        } else {
-            const double m2 = (double)ransac_count(job.pts, n, sst.a, sst.b, sst.c, sst.d, dadd((double)sst.depth_abs, 0.0001), smem_counts);
-            __syncthreads();
-            if (threadIdx.x == 0 && m2 > dadd(sst.maximum, dmul((double)n, 0.02))) {
-                sst.depth_abs = (float)((double)sst.depth_abs + 0.0001);
-                sst.maximum = m2;
+        for (int slice = task; slice < slices; slice += gridDim.x) {
+            if (planes_of != t) {
+                __syncthreads();
+                for (int h = threadIdx.x; h < c; h += blockDim.x) {
+                    double pa, pb, pc, pd;
+                    if (refine) ransac_perturbed_plane(job, st, f + h, pa, pb, pc, pd);
+                    else ransac_triple_plane(job, f + h, pa, pb, pc, pd);
+                    sm.pa[h] = pa; sm.pb[h] = pb; sm.pc[h] = pc; sm.pd[h] = pd;
+                }
+                planes_of = t;
             }
+            for (int h = threadIdx.x; h < c; h += blockDim.x) sm.cnt[h] = 0;
+            __syncthreads();
+            const int i = slice * kRansacSlice + threadIdx.x;
+            const bool valid = i < job.n;
+            const float3 p = job.pts[valid ? i : 0];
+            const double x = p.x, y = p.y, z = p.z, thr = (double)st.depth_abs;
+            const int lane = threadIdx.x & 31;
+            for (int h = 0; h < c; h++) {
+                const double r = fabs(dadd(dadd(dadd(dmul(x, sm.pa[h]), dmul(y, sm.pb[h])), dmul(z, sm.pc[h])), sm.pd[h]));
+                const unsigned bal = __ballot_sync(0xffffffffu, valid && r < thr);
+                if (lane == 0 && bal) atomicAdd(&sm.cnt[h], __popc(bal));
+            }
+            __syncthreads();
+            int *out = a.counts + (size_t)t * kRansacBatch;
+            for (int h = threadIdx.x; h < c; h += blockDim.x)
+                if (sm.cnt[h]) atomicAdd(&out[h], sm.cnt[h]);
+        }
+    }
+}
+
+// sequential phase, one CTA per region: walks the batch's counts in hypothesis order with the reference's acceptance rule
+// (>= replaces the best), applies the adaptive inlier threshold after hypotheses 0, 1000, 2000, ... (main.cpp:1645-1663),
+// or -- refinement -- commits the FIRST accepted perturbation and moves the cursor behind it (later trials of the round were
+// perturbations of the old best and are counted again from the new one).
+__device__ __forceinline__ void ransac_select_phase(const RansacFitArgs &a, RansacSmem &sm, int refine, int first, int count) {
+    for (int t = blockIdx.x; t < a.n_jobs; t += gridDim.x) {
+        const RansacJob job = a.jobs[t];
+        const int n = job.n;
+        int *cnt = a.counts + (size_t)t * kRansacBatch;
+        __syncthreads();
+        if (n <= 0) {
+            if (threadIdx.x == 0) a.states[t].cursor = kRefineTotal;
+            continue;
+        }
+        if (threadIdx.x == 0) {
+            RansacState st = a.states[t];
+            if (!refine) {
+                int best = -1;
+                for (int h = 0; h < count; h++)
+                    if ((double)cnt[h] >= st.maximum) { st.maximum = (double)cnt[h]; best = h; }
+                if (best >= 0) ransac_triple_plane(job, first + best, st.a, st.b, st.c, st.d);
+            } else {
+                const int base = st.cursor, m = min(count, kRefineTotal - base);
+                int hit = -1;
+                for (int h = 0; h < m; h++)
+                    if ((double)cnt[h] >= st.maximum) { hit = h; break; }
+                if (hit >= 0) {
+                    double pa, pb, pc, pd;
+                    ransac_perturbed_plane(job, st, base + hit, pa, pb, pc, pd);
+                    st.a = pa; st.b = pb; st.c = pc; st.d = pd; st.maximum = (double)cnt[hit];
+                    st.cursor = base + hit + 1;
+                } else {
+                    st.cursor = base + max(m, 0);
+                }
+            }
+            sm.st = st;
         }
         __syncthreads();
+        // the adaptive threshold step follows hypothesis k whenever k % 1000 == 0; batches end exactly there
+        if (!refine && ((first + count - 1) % 1000) == 0) {
+            const double rat = sm.st.maximum / (double)n;
+            if (rat < 0.3 && (double)sm.st.depth_abs < 0.003) {
+                __syncthreads();
+                if (threadIdx.x == 0) sm.st.depth_abs = (float)((double)sm.st.depth_abs + 0.0001);
+            } else {
+                const double m2 = (double)ransac_count(job.pts, n, sm.st.a, sm.st.b, sm.st.c, sm.st.d, dadd((double)sm.st.depth_abs, 0.0001), sm.warp_counts);
+                __syncthreads();
+                if (threadIdx.x == 0 && m2 > dadd(sm.st.maximum, dmul((double)n, 0.02))) {
+                    sm.st.depth_abs = (float)((double)sm.st.depth_abs + 0.0001);
+                    sm.st.maximum = m2;
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            a.states[t] = sm.st;
+            *job.out = make_float4((float)sm.st.a, (float)sm.st.b, (float)sm.st.c, (float)sm.st.d);
+        }
+        for (int h = threadIdx.x; h < kRansacBatch; h += blockDim.x) cnt[h] = 0;
     }
-    if (threadIdx.x == 0) {
-        states[blockIdx.x] = sst;
-        *job.out = make_float4((float)sst.a, (float)sst.b, (float)sst.c, (float)sst.d);
+}
+
+__global__ void __launch_bounds__(kRansacSlice) ransac_fit_kernel(const RansacFitArgs a) {
+    __shared__ RansacSmem sm;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_jobs; t += gridDim.x * blockDim.x) {
+        RansacState s;
+        s.a = 0; s.b = 0; s.c = 1; s.d = -1; s.maximum = 0;
+        s.depth_abs = (float)(0.0003 * (double)sqrtf(a.jobs[t].size / 20.0f));  // main.cpp:1552-1553
+        s.cursor = a.jobs[t].n > 0 ? 0 : kRefineTotal;
+        a.states[t] = s;
     }
-    for (int h = threadIdx.x; h < kRansacBatch; h += blockDim.x) cnt[h] = 0;
+    grid.sync();
+    // RANSAC hypotheses: the inlier threshold is constant between hypotheses 1000 j + 1 and 1000 (j + 1)
+    for (int first = 0; first < kRansacIters;) {
+        const int count = first == 0 ? 1 : min(kRansacBatch, kRansacIters - first);
+        ransac_count_phase(a, sm, 0, first, count);
+        grid.sync();
+        ransac_select_phase(a, sm, 0, first, count);
+        grid.sync();
+        first += count;
+    }
+    // local refinement, until every region has tried its 4000 perturbations
+    for (;;) {
+        bool done = true;
+        for (int t = 0; t < a.n_jobs; t++) done = done && (a.states[t].cursor >= kRefineTotal);
+        if (done) break;
+        ransac_count_phase(a, sm, 1, 0, kRefineSpec);
+        grid.sync();
+        ransac_select_phase(a, sm, 1, 0, kRefineSpec);
+        grid.sync();
+    }
 }
 
 }  // namespace tsar

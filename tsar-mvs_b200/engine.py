@@ -107,17 +107,52 @@ class DepthmapEngine:
         lab = np.ascontiguousarray(labels_q, np.int32)
         self._ck(self.lib.tsar_set_labels_quarter(self.h, lab.ctypes.data, lab.shape[1], lab.shape[0]), "tsar_set_labels_quarter")
 
-    def fit_region_planes(self, region_text, region_size, rnd, region_norm4):
-        """Per-region RANSAC plane fit (main.cpp:1520-1730) for regions with text == -1; rnd: [n_regions][46000]
-        uint32 (the values rand() would return).  Returns the updated [n_regions][4] planes."""
+    def scale_from_confidence(self, threshold=0.8):
+        """lines->scale = (confid > threshold): stands in for APD's weak.png when PatchMatch runs in the library."""
+        self._ck(self.lib.tsar_scale_from_confidence(self.h, float(threshold)), "tsar_scale_from_confidence")
+
+    def scale_from_weak_png(self, bgr):
+        """lines->scale from the decoded APD/<view>/weak.png (H x W x 3 uint8, BGR): main.cpp:1499-1514."""
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        if bgr.shape != (self.H, self.W, 3):
+            raise TsarError(f"weak.png is {bgr.shape}, expected {(self.H, self.W, 3)}")
+        self._ck(self.lib.tsar_scale_from_weak_png(self.h, bgr.ctypes.data), "tsar_scale_from_weak_png")
+
+    def download_outputs(self, depth=None, normals=None, confid=None):
+        """File payloads after compute_disp: depth [H][W], normals [H][W][3], confidence [H][W] (numpy arrays or raw
+        addresses of host buffers of those sizes; missing ones are allocated).  Returns (depth, normals, confid)."""
+        def buf(a, shape):
+            return np.empty(shape, np.float32) if a is None else a
+        depth, normals, confid = buf(depth, (self.H, self.W)), buf(normals, (self.H, self.W, 3)), buf(confid, (self.H, self.W))
+        ptr = lambda a: a if isinstance(a, int) else a.ctypes.data
+        self._ck(self.lib.tsar_download_outputs(self.h, ptr(depth), ptr(normals), ptr(confid)), "tsar_download_outputs")
+        return depth, normals, confid
+
+    def fit_region_planes(self, region_text, region_size, rnd, region_norm4, seed=None):
+        """Per-region RANSAC plane fit (main.cpp:1520-1730) for regions with text == -1.  rnd: [n_regions][46000] uint32
+        (the values rand() would return), or None to let the device generate the stream of `seed`
+        (tsar_fit_region_planes_seeded).  Returns the updated [n_regions][4] planes."""
         text = np.ascontiguousarray(region_text, np.float32)
         size = np.ascontiguousarray(region_size, np.float32)
+        planes = np.ascontiguousarray(region_norm4, np.float32).reshape(len(text), 4).copy()
+        if rnd is None:
+            self._ck(self.lib.tsar_fit_region_planes_seeded(self.h, len(text), text.ctypes.data, size.ctypes.data, int(seed or 0),
+                                                            planes.ctypes.data), "tsar_fit_region_planes_seeded")
+            return planes
         per = self.lib.tsar_ransac_rand_per_region()
         rnd = np.ascontiguousarray(rnd, np.uint32).reshape(len(text), per)
-        planes = np.ascontiguousarray(region_norm4, np.float32).reshape(len(text), 4).copy()
         self._ck(self.lib.tsar_fit_region_planes(self.h, len(text), text.ctypes.data, size.ctypes.data, rnd.ctypes.data,
                                                  planes.ctypes.data), "tsar_fit_region_planes")
         return planes
+
+    def ransac_rand_stream(self, seed, region):
+        """The device stream of tsar_fit_region_planes_seeded for one region (host restatement, for checkers)."""
+        per = self.lib.tsar_ransac_rand_per_region()
+        z = (np.uint64(seed) ^ (np.uint64(region) << np.uint64(32)) ^ np.arange(per, dtype=np.uint64)) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+        return (z >> np.uint64(33)).astype(np.uint32)
 
     # -- PatchMatch path ---------------------------------------------------------------------------
     def init_planes(self, seed):                      # gipuma_init_cu2

@@ -16,6 +16,10 @@ CONFIGS = {
     "C2": dict(W=3100, H=2050, n_images=11, V=10, fx=1750.0, radius=4.0, arc_deg=30.0),    # ETH3D pipes-shaped
     "C4": dict(W=1920, H=1080, n_images=11, V=10, fx=1160.0, radius=5.0, arc_deg=30.0),    # Tanks&Temples-shaped
     "C5": dict(W=6048, H=4032, n_images=21, V=20, fx=3410.0, radius=6.0, arc_deg=40.0),    # full-resolution stress
+    # multi-view datasets: a fixed set of reference views, each paired with its 10 nearest cameras (pair.txt)
+    "C3": dict(W=3100, H=2050, n_images=38, V=10, fx=1750.0, radius=4.0, arc_deg=44.0, rig="two_arcs"),   # ETH3D courtyard-shaped
+    "C4seq": dict(W=1920, H=1080, n_images=300, V=10, fx=1160.0, radius=5.0, arc_deg=60.0, rig="sequence"),  # Tanks&Temples-shaped
+    "C3small": dict(W=320, H=240, n_images=8, V=4, fx=800.0, radius=1.0, arc_deg=24.0, rig="two_arcs"),      # tests
     "mid": dict(W=1280, H=960, n_images=5, V=4, fx=720.0, radius=4.0, arc_deg=16.0),       # detector + completion tests
     "tiny": dict(W=96, H=64, n_images=4, V=3, fx=180.0, radius=1.0, arc_deg=16.0),         # unit tests / golden
     "small": dict(W=320, H=240, n_images=6, V=5, fx=800.0, radius=1.0, arc_deg=20.0),      # GPU parity tests
@@ -79,6 +83,47 @@ def make_cameras(W, H, n_images, fx, radius, arc_deg, depth_range=(0.7, 1.45), r
     for c, R, C in zip(cams, Rs, Cs):
         c["_R_world"], c["_C_world"] = R, C
     return cams
+
+
+def make_rig(cfg):
+    """World cameras of a multi-view dataset (every image is a reference view once, scripts/pipes.sh:30-49):
+      two_arcs  n/2 cameras on each of two arcs at different heights (ETH3D courtyard-shaped: a photographer walking
+                along the scene twice);
+      sequence  n cameras along one arc with a slow vertical wave (Tanks&Temples-shaped video sequence).
+    Returns (K, [R], [C], neighbours) with neighbours[i] = the V cameras nearest to camera i, nearest first (pair.txt)."""
+    W, H, n, fx, radius = cfg["W"], cfg["H"], cfg["n_images"], cfg["fx"], cfg["radius"]
+    K = np.array([[fx, 0, (W - 1) / 2.0], [0, fx, (H - 1) / 2.0], [0, 0, 1.0]])
+    half = np.deg2rad(cfg["arc_deg"]) / 2.0
+    Cs = []
+    if cfg["rig"] == "two_arcs":
+        per = (n + 1) // 2
+        for i in range(n):
+            row, k = divmod(i, per)
+            a = -half + 2 * half * (k + 0.5 * row) / max(per - 1 + 0.5, 1)
+            Cs.append(radius * np.array([np.sin(a), (-0.10 if row == 0 else 0.12), -np.cos(a)]))
+    else:
+        for i in range(n):
+            a = -half + 2 * half * i / max(n - 1, 1)
+            Cs.append(radius * np.array([np.sin(a), 0.08 * np.sin(0.21 * i), -np.cos(a)]))
+    Rs = [_look_at(C, np.zeros(3)) for C in Cs]
+    P = np.stack(Cs)
+    d = np.linalg.norm(P[:, None, :] - P[None, :, :], axis=-1)
+    neighbours = [[int(j) for j in np.argsort(d[i], kind="stable") if j != i][:cfg["V"]] for i in range(n)]
+    return K, Rs, Cs, neighbours
+
+
+def render_rig(cfg, seed=1234, backend="numpy", device=None, depth_range=(0.7, 1.45)):
+    """Images of all cameras of a rig (uint8), generator of (index, image).  Depth range as make_cameras."""
+    K, Rs, Cs, _ = make_rig(cfg)
+    sc = Scene(cfg["W"], cfg["H"], cfg["fx"], cfg["radius"], seed=seed)
+    Kinv = np.linalg.inv(K)
+    for i, (R, C) in enumerate(zip(Rs, Cs)):
+        cam = dict(K_inv=Kinv, _R_world=R, _C_world=C)
+        if backend == "torch":
+            img = sc.render_torch(cam, cfg["W"], cfg["H"], device)[0].cpu().numpy().astype(np.uint8)
+        else:
+            img = sc.render(cam, cfg["W"], cfg["H"])[0]
+        yield i, img
 
 
 class Scene:
