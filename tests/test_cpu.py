@@ -197,8 +197,18 @@ def test_view_sharding_partitions(pkg):
         parts = [shard.views_for_rank(n, r, w) for r in range(w)]
         assert sorted(sum(parts, [])) == list(range(n))
         assert max(map(len, parts)) - min(map(len, parts)) <= 1
+        blocks = [shard.block_for_rank(n, r, w) for r in range(w)]
+        assert sum(blocks, []) == list(range(n))                                  # contiguous, in order
+        assert max(map(len, blocks)) - min(map(len, blocks)) <= 1
     with pytest.raises(ValueError):
         shard.views_for_rank(3, 2, 2)
+    with pytest.raises(ValueError):
+        shard.block_for_rank(3, 2, 2)
+    # blocks keep a rank's image pool small: 38 courtyard views on 8 ranks, 10 nearest neighbours each
+    K, Rs, Cs, nb = pkg.scene.make_rig(pkg.scene.CONFIGS["C3"])
+    need_block = max(len(set(b) | {j for i in b for j in nb[i]}) for b in (shard.block_for_rank(38, r, 8) for r in range(8)))
+    need_rr = max(len(set(b) | {j for i in b for j in nb[i]}) for b in (shard.views_for_rank(38, r, 8) for r in range(8)))
+    assert need_block <= 26 and need_rr >= 36
 
 
 def _gloo_worker(rank, world, port, q):

@@ -26,8 +26,8 @@ Extra: `--synthetic=<C1|C2|small|tiny>` first writes a synthetic dataset in the 
 `-all_views` replaces the per-view process loop of the run scripts (scripts/pipes.sh:30-49): every image of the
 dataset becomes the reference view once.  All images are decoded and uploaded ONCE and stay resident in HBM; each
 reference view binds itself + its pair.txt neighbours from that pool (device-to-device), two contexts on two streams
-pipeline view r+1 behind view r, results are written by the worker threads.  Under torchrun the views are sharded
-round-robin over the ranks (shard.py), one GPU per rank, no collective.
+pipeline view r+1 behind view r, results are written by a writer pool.  Under torchrun the views are sharded in
+contiguous blocks over the ranks (shard.py), one GPU per rank, no collective.
 """
 import os
 import sys
@@ -154,9 +154,10 @@ def write_synthetic_dataset(cfg_name, root):
     return sc, names
 
 
-def write_rig_dataset(cfg_name, root, backend="numpy", device=None, png_compression=1):
+def write_rig_dataset(cfg_name, root, backend="numpy", device=None, jpeg_quality=95):
     """A multi-view synthetic dataset (scene.make_rig: C3 = 38 cameras on two arcs, C4seq = 300-frame sequence) in the
-    reference's folder layout; pair.txt lists every camera's 10 nearest neighbours.  Returns the image names."""
+    reference's folder layout, images as JPEG files like the ETH3D / Tanks&Temples originals (scripts/*.sh list
+    %08d.jpg names); pair.txt lists every camera's 10 nearest neighbours.  Returns the image names."""
     import cv2
     cfg = scene.CONFIGS[cfg_name]
     K, Rs, Cs, neighbours = scene.make_rig(cfg)
@@ -164,8 +165,8 @@ def write_rig_dataset(cfg_name, root, backend="numpy", device=None, png_compress
     os.makedirs(os.path.join(root, "cams"), exist_ok=True)
     names = []
     for i, img in scene.render_rig(cfg, backend=backend, device=device):
-        name = f"{i:08d}.png"
-        cv2.imwrite(os.path.join(root, "images", name), img, [cv2.IMWRITE_PNG_COMPRESSION, int(png_compression)])
+        name = f"{i:08d}.jpg"
+        cv2.imwrite(os.path.join(root, "images", name), img, [cv2.IMWRITE_JPEG_QUALITY, int(jpeg_quality)])
         R, C = Rs[i], Cs[i]
         write_cam_txt(os.path.join(root, "cams", f"{i:08d}_cam.txt"), K, R, -R @ C, 0.7 * cfg["radius"], 1.45 * cfg["radius"])
         names.append(name)
@@ -357,7 +358,7 @@ def run_all_views(opt, mslp, quiet=False):
     import torch
 
     from .engine import cameras_to_struct
-    from .shard import views_for_rank
+    from .shard import block_for_rank
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     ndev = torch.cuda.device_count()
     if ndev == 0:
@@ -370,7 +371,7 @@ def run_all_views(opt, mslp, quiet=False):
     t0 = time.perf_counter()
     krt = [read_cam_txt(os.path.join(mslp, "cams", f"{n[:8]}_cam.txt")) for n in names]
     pairs = read_pair_table(os.path.join(mslp, "pair.txt"))
-    mine = views_for_rank(len(names), rank, world)
+    mine = block_for_rank(len(names), rank, world)      # contiguous blocks: neighbouring views share their source images
     neigh = {r: [by_id[c] for c in pairs.get(ids[r], []) if c in by_id] for r in mine}
     needed = sorted(set(mine) | {i for r in mine for i in neigh[r]})
     want_colour = not opt["no_slic"]

@@ -58,6 +58,7 @@ struct tsar_ctx {
     int *d_flag = nullptr;
     int use_u8 = 0;                            // every image is 8-bit valued: sample the 8-bit textures
     bool allow_u8 = true;                      // env TSAR_B200_NO_U8=1 switches the fast path off
+    bool u8_verified = false, u8_ok = false;   // one-time self-check of the 8-bit sampling identity (tsar_set_views)
     int arr_w = 0, arr_h = 0;
     float *ref_img = nullptr;
     cudaTextureObject_t *d_tex = nullptr;
@@ -127,6 +128,23 @@ __global__ void to_u8_kernel(const float *__restrict__ img, unsigned char *__res
     const bool ok = (v == r) && (v >= 0.0f) && (v <= 255.0f);
     out[i] = ok ? (unsigned char)r : 0;
     if (!ok) *flag = 1;
+}
+
+// Self-check of the 8-bit sampling identity: 4096 pseudo-random coordinates (an eighth of them pushed onto the image
+// border, where clamp addressing acts) sampled through the fp32 texture and through the 8-bit copy; the 8-bit result,
+// snapped as view_cost snaps it (N = rint(v * 255 * 256), value N / 256), must equal the fp32 sample bit for bit.
+__global__ void u8_selfcheck_kernel(cudaTextureObject_t tex32, cudaTextureObject_t tex8, int W, int H, int *mismatches) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned h = i * 2654435761u + 12345u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    const unsigned g = h * 3266489917u + 1u;
+    float x = (float)(h % (unsigned)(W * 64)) / 64.0f, y = (float)((g >> 4) % (unsigned)(H * 64)) / 64.0f;
+    if ((i & 7u) == 0u) { x = (i & 8u) ? -1.37f : (float)W + 0.61f; }
+    if ((i & 7u) == 1u) { y = (i & 8u) ? -0.73f : (float)H + 1.29f; }
+    const float a = tex2D<float>(tex32, x, y);
+    const float v = tex2D<float>(tex8, x, y);
+    const float n = __fsub_rn(__fmaf_rn(v, 65280.0f, 12582912.0f), 12582912.0f);
+    if (__float_as_uint(__fmul_rn(n, 0.00390625f)) != __float_as_uint(a)) atomicAdd(mismatches, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -464,7 +482,7 @@ int tsar_set_views(tsar_ctx *ctx, int W, int H, int n_images, const float *const
         }
         CK(cudaMalloc(&ctx->stage8, n));
     }
-    if (!ctx->d_flag) CK(cudaMalloc(&ctx->d_flag, sizeof(int)));
+    if (!ctx->d_flag) CK(cudaMalloc(&ctx->d_flag, 2 * sizeof(int)));
     // host images cross the bus once, into a persistent linear staging buffer (no per-call cudaMalloc/cudaFree: those
     // synchronise the whole device and would serialise contexts that pipeline views on other streams)
     if (!on_device && ctx->stage32_n < n) {
@@ -472,7 +490,7 @@ int tsar_set_views(tsar_ctx *ctx, int W, int H, int n_images, const float *const
         CK(cudaMalloc(&ctx->stage32, n * 4));
         ctx->stage32_n = n;
     }
-    CK(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int), ctx->stream));
     for (int i = 0; i < n_images; i++) {
         const float *src = images[i];
         if (!on_device) {
@@ -489,12 +507,6 @@ int tsar_set_views(tsar_ctx *ctx, int W, int H, int n_images, const float *const
             ctx->launches++;
         }
     }
-    if (ctx->allow_u8) {
-        int flag = 1;
-        CK(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        ctx->use_u8 = (flag == 0);
-    }
     ctx->W = W; ctx->H = H; ctx->n_images = n_images; ctx->V = V;
     ctx->cams.assign(cams, cams + n_images);
     ctx->cam_f = cam_f;
@@ -505,7 +517,25 @@ int tsar_set_views(tsar_ctx *ctx, int W, int H, int n_images, const float *const
         for (int k = 0; k < 3; k++) cd[i].t[k] = cams[i].t4[k];
     }
     CK(cudaMemcpyAsync(ctx->d_cams, cd.data(), n_images * sizeof(CamDev), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));  // cd / caller buffers may go away
+    // The 8-bit fast path rests on how the texture unit quantises its bilinear weights (pm_core.cuh, view_cost): checked
+    // once per context on this device and driver, on the reference image incl. its borders, against the fp32 texture.
+    int *flags = ctx->d_flag;   // [0] some image is not 8-bit valued, [1] mismatches of the self-check
+    const bool check = ctx->allow_u8 && !ctx->u8_verified;
+    if (check) {
+        u8_selfcheck_kernel<<<16, 256, 0, ctx->stream>>>(ctx->tex[0], ctx->tex8[0], W, H, flags + 1);
+        ctx->launches++;
+    }
+    int host_flags[2] = {1, 0};
+    if (ctx->allow_u8) CK(cudaMemcpyAsync(host_flags, flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // one wait per call: the flags are needed now, and cd / the caller's buffers may go away
+    if (ctx->allow_u8) {
+        if (check && host_flags[0] == 0) {     // (only meaningful when the image really is 8-bit valued)
+            ctx->u8_verified = true;
+            ctx->u8_ok = host_flags[1] == 0;
+            if (!ctx->u8_ok) fprintf(stderr, "[tsar_b200] 8-bit texture self-check failed on this device/driver (%d of 4096 samples differ): sampling fp32 textures\n", host_flags[1]);
+        }
+        ctx->use_u8 = (host_flags[0] == 0) && ctx->u8_verified && ctx->u8_ok;
+    }
     // XORWOW row table: W draws of offset + head-room for the Marsaglia rejection loop / 4 draws per refine round
     ctx->rng_len = W + 192;
     ctx->rng_pitch = (ctx->rng_len + 31) & ~31;
@@ -688,6 +718,7 @@ int tsar_compute_disp(tsar_ctx *ctx) {
     compute_disp_kernel<<<g, b, 0, ctx->stream>>>(ctx->glue, ctx->plane[0], ctx->cost[0]);
     ctx->launches++;
     CK(cudaGetLastError());
+    ctx->have_planes = false;   // buffer 0 now holds the OUTPUT layout (world normal, depth in w), not (n, d) planes
     return TSAR_OK;
 }
 
@@ -701,7 +732,7 @@ int tsar_update_scale(tsar_ctx *ctx) {
                                                   ctx->region_text, ctx->region_plane, ctx->n_regions);
     ctx->launches++;
     CK(cudaGetLastError());
-    return TSAR_OK;
+    return seed_alt_buffers(ctx);   // rows outside the checkerboard grid live in both buffers
 }
 
 int tsar_update_scale_2(tsar_ctx *ctx) {
@@ -745,7 +776,8 @@ int tsar_wmf_final(tsar_ctx *ctx, int iter) {
                           ctx->region_text, ctx->n_regions, iter, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
-    return rc;
+    if (rc) return rc;
+    return seed_alt_buffers(ctx);
 }
 
 int tsar_set_regions(tsar_ctx *ctx, int n_regions, const float *text, const float *norm4) {
@@ -1006,6 +1038,8 @@ int tsar_download(tsar_ctx *ctx, int field, void *dst, size_t bytes) {
 
 int tsar_device_ptr(tsar_ctx *ctx, int field, void **dev_ptr) {
     if (!ctx || !dev_ptr) return TSAR_ERR_ARG;
+    if (!ctx->have_views) FAIL(TSAR_ERR_STATE, "tsar_set_views has not been called");
+    CK(cudaSetDevice(ctx->device));
     if (field == TSAR_F_NORM4 || field == TSAR_F_COST) {
         int rc = consolidate(ctx);
         if (rc) return rc;

@@ -76,7 +76,8 @@ __global__ void slic_init_centers_kernel(const float4 *__restrict__ lab, SpixelI
 }
 
 // find_center_association_shared + compute_slic_distance (shared.h:92-134): argmin over the 3x3 neighbouring
-// centres, strict <, first wins.  The <= 9 candidate centres of a 16x16 pixel tile are staged in shared memory.
+// centres, strict <, first wins.  The <= 9 candidate centres are read straight from global memory (32-byte records,
+// a few hundred of them: they live in L1/L2; the kernel takes 14 us at C2).
 __global__ void slic_assign_kernel(const float4 *__restrict__ lab, const SpixelInfo *__restrict__ sp, int *__restrict__ idx,
                                    int mw, int mh, int w, int h, int size, float weight, float norm_xy) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;

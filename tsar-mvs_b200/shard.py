@@ -10,6 +10,17 @@ def views_for_rank(n_views, rank, world):
     return list(range(rank, n_views, world))
 
 
+def block_for_rank(n_views, rank, world):
+    """Contiguous assignment: rank r gets views [start, start + count) with counts differing by at most one.  Views that
+    are neighbours in the list (capture order) share most of their pair.txt source views, so a rank decodes and keeps
+    resident little more than its own block -- what the multi-view driver uses (cli.run_all_views)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, extra = divmod(n_views, world)
+    start = rank * base + min(rank, extra)
+    return list(range(start, start + base + (1 if rank < extra else 0)))
+
+
 def gather_results(local, world, group=None):
     """Optional terminal gather of {view_id: ndarray} dicts to rank 0 (torch.distributed object gather; gloo or
     nccl).  Not on the hot path."""
