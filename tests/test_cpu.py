@@ -245,7 +245,11 @@ def test_bench_reference_arm_contract():
     """bench.py parses; --impl reference without a GPU is out of scope here (needs the B200), but the ratio inputs
     (metric, unit, higher_is_better) must be identical strings in both arms."""
     src = open(os.path.join(ROOT, "bench.py")).read()
-    assert src.count('"metric": "depthmaps/s"') == 2 and src.count('"higher_is_better": True') == 2
+    # three emitters: our arm, the reference arm, the multi-view product driver (--config C3 / C4)
+    assert src.count('"metric": "depthmaps/s"') == 3 and src.count('"higher_is_better": True') == 3
+    assert src.count('"config": config_dict(args.config, cfg, iters, args.blocksize, world)') == 2   # identical dicts in both arms
+    ref_arm = src[src.index("def run_reference(args):"):src.index('if __name__ == "__main__":')]
+    assert "DepthmapEngine" not in ref_arm and "_lib.load" not in ref_arm   # the product library stays out of the reference arm
 
 
 def test_abi_layout_matches_reference(tmp_path):
