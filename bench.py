@@ -309,12 +309,14 @@ def run_ours(args):
     flops_eval = 40.0 * n_samp + 150.0                              # BASELINE.md section 3 (1590 at S = 36)
     achieved = evals_checker * flops_eval / (avg_ms * 1e-3) / 1e12
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_dram_bytes.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.config)
-        except Exception:
-            traffic = None
+    for tname in ("r02_dominant_kernel_dram_bytes.json", "r01_dominant_kernel_dram_bytes.json"):   # one ncu --set full capture per round
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.config)
+            except Exception:
+                traffic = None
+            break
     peaks_file = {}
     try:
         peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

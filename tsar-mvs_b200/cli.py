@@ -208,8 +208,11 @@ def run_view(eng, opt, view, outputs=None):
             np.array([(labels == r).sum() / 16.0 for r in range(len(text))], np.float32)
         eng.upload(L.F_CANNY, labels)
     elif not opt["no_weak_texture"]:            # texture() runs first in the reference's main (main.cpp:1893)
+        import time
         from . import texture
+        t_det = time.perf_counter()
         det = texture.detect(view["gray_u8"])
+        info["detect_s"] = time.perf_counter() - t_det
         info["regions"], info["weak_regions"] = len(det["text"]) - 1, int((det["text"] == -1).sum())
         text, size = det["text"], det["size"]
         eng.set_labels_quarter(det["labels_q"])
@@ -467,7 +470,8 @@ def run_all_views(opt, mslp, quiet=False):
         view = dict(gray_u8=u8, bgr=bgr, apd_dir=out_dir, seed=int(opt["seed"]) + r, cam_f=f)
         t = time.perf_counter()
         _, _, _, info = run_view(eng, opt, view, outputs=tuple(b.data_ptr() + 16 for b in bufs))
-        add("gpu_wait_s", time.perf_counter() - t)
+        add("detect_s", info.get("detect_s", 0.0))      # host stage of run_view (weak-texture detector)
+        add("gpu_wait_s", time.perf_counter() - t - info.get("detect_s", 0.0))
         infos[r] = {k_: v for k_, v in info.items() if k_ != "slic_labels"}
         if opt["no_write"]:
             lane["free"].put(bufs)
