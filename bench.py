@@ -355,6 +355,17 @@ def run_ours(args):
         "gevals_per_s": world * args.steps * n_evals / (ms * 1e-3) / 1e9, "evals_per_depthmap": n_evals,
         "roofline": roofline, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
     }
+    # executed evaluations counted on the device (debug counter, tools/gpu_cand_stats.py) next to the as-written closed form
+    spath = os.path.join(ROOT, "profiles", f"r02_candidate_stats_{args.config}.json")
+    if os.path.exists(spath) and args.blocksize == 11:
+        try:
+            st = json.load(open(spath))
+            out["evals_executed"] = {"as_written_closed_form": st["closed_form_evaluations"], "executed_device_counter": st["executed_evaluations_as_written"],
+                                     "distinct_hypotheses_only": st["executed_evaluations_skipping_duplicates"],
+                                     "roofline_frac_on_executed": roofline["frac"] * st["executed_evaluations_as_written"] / st["closed_form_evaluations"]
+                                     if roofline["frac"] else None, "source": os.path.relpath(spath, ROOT)}
+        except Exception:
+            pass
     if world == 1 and not args.no_cpu_baseline:
         try:
             out["cpu_baseline"] = cpu_baseline(pkg, cfg, n_evals)
@@ -395,14 +406,15 @@ def run_product(args):
     os.environ["LOCAL_RANK"] = str(local)
     results = []
     for _ in range(max(args.warmup, 1) if args.warmup else 0):
-        pkg.cli.run_all_views(dict(opt, images=sorted(os.listdir(root + "images"))[:world * 2]), root, quiet=True)   # warm-up: two views per rank
+        # warm-up: two views per rank; the driver is persistent (contexts and pinned buffers stay alive between passes)
+        pkg.cli.run_all_views(dict(opt, views_per_rank=2), root, quiet=True, persistent=True)
     secs = []
     with ClockSampler(local, enabled=(rank == 0)) as clk:
         for k in range(args.steps):
             shutil.rmtree(os.path.join(root, "APD"), ignore_errors=True) if rank == 0 else None
             barrier(world)
             t0 = time.perf_counter()
-            res = pkg.cli.run_all_views(opt, root, quiet=True)
+            res = pkg.cli.run_all_views(opt, root, quiet=True, persistent=True)
             torch.cuda.synchronize()
             dt_local = time.perf_counter() - t0
             barrier(world)
@@ -437,6 +449,7 @@ def run_product(args):
             "clocks": clk.summary(),
         }
         print(json.dumps(out), flush=True)
+    pkg.cli.release_lanes()
     barrier(world)
     if rank == 0:
         shutil.rmtree(root, ignore_errors=True)

@@ -850,6 +850,21 @@ def test_cli_all_views_resident_pool(env, tmp_path):
         assert os.path.exists(os.path.join(root, "APD", f"{v:08d}", "TSAR_confidence.dmb"))
     assert pc.frac_bit_exact(dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_disp.dmb")), one) == 1.0
     assert pc.frac_bit_exact(dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_normals.dmb")), one_n) == 1.0
+    # the persistent driver (contexts and pinned buffers kept between passes, as the benchmark's passes do): a warm-up
+    # pass over two views and two full passes in this process write the same files again
+    import shutil
+    ref_files = {v: dmb.read_dmb(os.path.join(root, "APD", f"{v:08d}", "TSAR_normals.dmb")) for v in range(n)}
+    opt = pkg.cli.parse_args(["-all_views", "-images_folder", root + "images/"] + common)
+    pkg.cli.run_all_views(dict(opt, views_per_rank=2), root, quiet=True, persistent=True)
+    for _ in range(2):
+        shutil.rmtree(os.path.join(root, "APD"))
+        res = pkg.cli.run_all_views(opt, root, quiet=True, persistent=True)
+        assert res["views"] == n and res["gpu_launches"] > 0
+        for v in range(n):
+            assert pc.frac_bit_exact(dmb.read_dmb(os.path.join(root, "APD", f"{v:08d}", "TSAR_normals.dmb")), ref_files[v]) == 1.0
+    assert len(pkg.cli._LANE_POOL) == 1
+    pkg.cli.release_lanes()
+    assert not pkg.cli._LANE_POOL
 
 
 def test_labels_quarter_expansion_on_device(env):

@@ -5,12 +5,16 @@
 // about 7e8 double residuals per region on one CPU core in the reference.
 //
 // Here: device-side stable compaction of the region's reliable pixels (raster order, as the reference collects
-// them), back-projection, then batches of hypotheses counted by the whole GPU (ransac_batch_count_kernel: a CTA owns
-// 256 points and runs through the batch) with the loop-carried part -- best-so-far, adaptive threshold, commit of the
-// first accepted perturbation -- in a one-CTA-per-region kernel between the batches (ransac_select_kernel).  All arithmetic is IEEE double without contraction, in the reference's evaluation
-// order, so the result is bit-identical to a scalar C restatement given the same random numbers.  The reference
+// them), back-projection, then ONE persistent cooperative kernel (ransac_fit_kernel) fits all textureless regions of the
+// view: hypotheses are counted in batches by the whole grid (count phase: a CTA keeps a 256-point slice of one region in
+// registers as doubles and runs through the <= 1000 planes of the batch from shared memory; per-warp ballots, shared
+// then global atomics), and between two grid.sync() one CTA per region applies the loop-carried rules (select phase:
+// best-so-far, adaptive threshold, commit of the first accepted perturbation and the cursor behind it).  The loop ends on
+// the device; the host waits once, for the result.  Scratch lives in the context (grow-only).  All arithmetic is IEEE
+// double without contraction, in the reference's evaluation order, so the result is bit-identical to the reference's own
+// loop (main.cpp:1520-1730 compiled by oracle/build_ref.sh) given the same random numbers.  The reference
 // draws them from rand()/system_clock (not reproducible); the caller supplies the stream instead (the values
-// rand() would have returned, 46 000 per region), which also makes the fit testable.
+// rand() would have returned, 46 000 per region) or a seed for a device-generated stream (ransac_rand_kernel).
 // Kept quirks: the A coefficient of calcLinePara uses (y3-y1) twice (main.cpp:159); ties (>=) replace the best.
 // Deviation: when a region has more than 49 999 reliable pixels the reference keeps a random subset
 // (std::shuffle with a clock seed); we keep an evenly strided subset.
