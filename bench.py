@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--blocksize", type=int, default=11, help="NCC window (the run scripts use 11; the reference's built-in default is 19)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "engine", "driver"],
+                    help="engine: one reference-view stream per GPU, inputs resident (C1, C2, C4, C5); driver: a fixed view set through the "
+                         "multi-view file driver (C3, C4 = 300 views); auto: driver for C3 / C4, engine otherwise")
     ap.add_argument("--lanes", type=int, default=2, help="pipelined contexts per GPU of the multi-view driver (--config C3 / C4)")
     ap.add_argument("--io_threads", type=int, default=6, help="decoder / writer threads per rank of the multi-view driver")
     return ap.parse_args()
@@ -542,13 +545,16 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference" and a.config in PRODUCT_CONFIGS:
+    driver = a.config in PRODUCT_CONFIGS and a.mode != "engine"
+    if a.mode == "driver" and a.config not in PRODUCT_CONFIGS:
+        sys.exit(f"--mode driver needs one of {sorted(PRODUCT_CONFIGS)}")
+    if a.impl == "reference" and driver:
         if int(os.environ.get("RANK", "0")) == 0:
             print(json.dumps({"impl": "reference", "unavailable": "the reference has no multi-view driver (one process per view, scripts/pipes.sh); "
                                                                    "its per-view rate is measured by --config C2 --impl reference"}), flush=True)
     elif a.impl == "reference":
         run_reference(a)
-    elif a.config in PRODUCT_CONFIGS:
+    elif driver:
         run_product(a)
     else:
         run_ours(a)

@@ -72,7 +72,18 @@ def main():
             rnd = rng.randint(0, 2 ** 31 - 1, size=(len(text), per)).astype(np.uint32)
             e.upload(L.F_DEPTH, (scene["cam_f"] / scene["gt_depth"]).astype(np.float32))
             e.upload(L.F_SCALE, (rng.rand(H, W) < 0.5).astype(np.float32))
-            e.fit_region_planes(text, size, rnd, np.tile(np.array([0, 0, 1, -1], np.float32), (len(text), 1)))
+            p0 = np.tile(np.array([0, 0, 1, -1], np.float32), (len(text), 1))
+            e.fit_region_planes(text, size, rnd, p0)
+            e.fit_region_planes(text, size, None, p0, seed=5)          # device-generated random stream
+            # reliable-pixel sources of the flows, quarter-resolution labels, candidate counters
+            e.scale_from_confidence(0.8)
+            png = np.zeros((H, W, 3), np.uint8); png[::2] = 255; png[1::4, :, 1] = 255
+            e.scale_from_weak_png(png)
+            e.set_labels_quarter(rng.randint(0, 5, size=((H + 3) // 4, (W + 3) // 4)).astype(np.int32))
+            e.init_planes(7)
+            for colour in (0, 1):
+                st = e.candidate_stats(colour)
+                assert st["distinct"] <= st["in_depth_range"] <= st["behind_border_guards"]
             # gSLICr, all modes
             bgr = scene["bgr"]
             bgrx = np.concatenate([bgr, np.zeros(bgr.shape[:2] + (1,), np.uint8)], -1)
