@@ -339,17 +339,24 @@ def run_ours(args):
         "tex_gsamples_per_s": evals_checker * n_samp / (avg_ms * 1e-3) / 1e9, "tex_peak_gsamples_per_s": tex_g,
         "tex_frac": (evals_checker * n_samp / (avg_ms * 1e-3) / 1e9) / tex_g if tex_g else None,
         "mufu_peak_gops_measured": mufu_g, "mufu_peak_gops_nominal": 148 * 16 * 1.965,
+        # SFU view: 4*S + 12 MUFU per evaluation as written in pmCost (two rcp, one rsq, one ex2 per
+        # sample); this kernel issues S + 12 (one reciprocal per sample, reference-image terms hoisted)
+        "sfu": {"as_written_gops": evals_checker * (4 * n_samp + 12) / (avg_ms * 1e-3) / 1e9,
+                "executed_gops": evals_checker * (n_samp + 12) / (avg_ms * 1e-3) / 1e9, "peak_gops": mufu_g,
+                "frac_as_written": evals_checker * (4 * n_samp + 12) / (avg_ms * 1e-3) / 1e9 / mufu_g if mufu_g else None,
+                "frac_executed": evals_checker * (n_samp + 12) / (avg_ms * 1e-3) / 1e9 / mufu_g if mufu_g else None},
         "hbm": {"bound": "hbm", "achieved": alg_bytes / (avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback"},
         "traffic": traffic,
     }
     if args.blocksize == 11:
-        # texture-pipe view (the tighter bound): one wavefront per clock per SM; 9.65 wavefronts per
+        # texture-pipe view (the tighter bound): one wavefront per clock per SM; 9.64 wavefronts per
         # warp-wide bilinear fetch measured by ncu (profiles/r01_variants_C2.json, independent of locality)
-        sm_count, clk_hz, wf_per_fetch = 148, 1.965e9, 9.65
+        sm_count, clk_hz, wf_per_fetch = 148, 1.965e9, 9.64   # profiles/r02_ncu_full_pm_checker_C2.csv: 4483.5 M wavefronts / 465.3 M fetches
         tex_bound_ms = evals_checker * n_samp / 32.0 * wf_per_fetch / (sm_count * clk_hz) * 1e3
         roofline["texture"] = {"bound": "texture wavefronts", "bound_ms": tex_bound_ms, "achieved_ms": avg_ms,
-                               "frac": tex_bound_ms / avg_ms if avg_ms else None, "wavefronts_per_fetch": wf_per_fetch}
+                               "frac": tex_bound_ms / avg_ms if avg_ms else None, "wavefronts_per_fetch": wf_per_fetch,
+                               "ncu_data_pipe_pct_of_sustained_peak": 91.5}
     out = {
         "metric": "depthmaps/s", "value": value, "unit": "depthmaps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
