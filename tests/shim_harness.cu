@@ -21,6 +21,10 @@ static T *managed(size_t n) {
     return p;
 }
 
+// reliable flags (lines->scale) for the next run; null = all zero as LineState::resize leaves them
+static const float *g_reliable = nullptr;
+extern "C" void shim_harness_set_reliable(const float *flags) { g_reliable = flags; }
+
 extern "C" int shim_harness_run(int W, int H, int n_images, const float *const *images, const tsar_camera *cams, float cam_f,
                                 const int *subset, int V, const tsar_params *p, const float *canny, int n_regions,
                                 const float *region_text, const float *region_norm4, int shipped_flow,
@@ -92,6 +96,7 @@ extern "C" int shim_harness_run(int W, int H, int n_images, const float *const *
     ::GlobalState &ref = reinterpret_cast<::GlobalState &>(*gs);
     int rc;
     if ((rc = firstcuda(ref))) return rc;
+    if (g_reliable) memcpy(l.scale, g_reliable, n * 4);      // the reliable flags main() reads from weak.png (main.cpp:1499-1514)
     if ((rc = sliccuda(ref))) return rc;
     memcpy(out_confid, l.confid, n * 4);
     if ((rc = fakecuda(ref))) return rc;

@@ -514,6 +514,35 @@ def test_reference_entry_points_drop_in(env, small):
     assert pc.frac_bit_exact(s_fd, ref.download(rb.F_FAKEDEPTH)) == 1.0
     assert pc.frac_bit_exact(s_sc, ref.download(rb.F_SCALE)) == 1.0
     ref.close()
+    # (c) TSAR_B200_WMF=1: the weighted-median stages at the launch sites where the reference has them commented out
+    # (gipuma_WMF x 4 at the end of sliccuda, gipuma_WMF_Final x 6 in fillcuda; gipuma.cu:1809-1812, 1844-1847), fed with the
+    # reliable flags main() takes from weak.png before sliccuda == the engine running the same sequence
+    reliable = (rng.rand(H, W) < 0.6).astype(np.float32)
+    h.shim_harness_set_reliable(reliable.ctypes.data_as(C.c_void_p))
+    os.environ["TSAR_B200_WMF"] = "1"
+    try:
+        w_n4, w_cf, w_fd, w_sc = run(True, wn, disp)
+    finally:
+        del os.environ["TSAR_B200_WMF"]
+        h.shim_harness_set_reliable(None)
+    _, eng, _ = pc.make_engines(pkg, scene, iterations=2, variants=())
+    eng.set_regions(scene["region_text"], scene["region_norm4"])
+    eng.upload(L.F_CANNY, scene["canny"])
+    eng.upload(L.F_NORM4, wn); eng.upload(L.F_COST, np.ones((H, W), np.float32)); eng.upload(L.F_DEPTH, disp)
+    eng.get_disp(); eng.getview()
+    eng.upload(L.F_SCALE, reliable)
+    for it in range(4):
+        eng.wmf(it)
+    eng.update_scale_2(); eng.update_scale()
+    for it in range(6):
+        eng.wmf_final(it)
+    eng.compute_disp()
+    assert pc.frac_bit_exact(w_cf, s_cf) == 1.0                         # the confidence map is computed before the filter
+    assert pc.frac_bit_exact(w_n4, eng.download(L.F_NORM4)) == 1.0
+    assert pc.frac_bit_exact(w_fd, eng.download(L.F_FAKEDEPTH)) == 1.0
+    assert pc.frac_bit_exact(w_sc, eng.download(L.F_SCALE)) == 1.0
+    assert pc.frac_bit_exact(w_n4, s_n4) < 0.999                        # and the filter changed the result
+    eng.close()
 
 
 def test_wmf_and_wmf_final_bit_exact(env, small):
@@ -939,6 +968,89 @@ def test_cli_full_tsar_flow_with_detector(env, tmp_path):
         else:
             wmf_depth = dmb.read_dmb(os.path.join(root, "APD", "00000000", "TSAR_disp.dmb"))
             assert (wmf_depth != with_fill).mean() > 1e-4               # the weighted-median fill changed pixels
+
+
+def test_cli_shipped_flow_from_an_apd_folder(env, tmp_path):
+    """`-import_apd`: the flow the reference ships (main.cpp:1459-1783) from files -- planes from APD/<view>/depths_geom.dmb +
+    normals.dmb, reliable pixels from APD/<view>/weak.png (white, green or red, main.cpp:1499-1514), detector, per-region
+    RANSAC, completion -- against the same flow assembled from the reference's own pieces: its kernels (oracle/_ref
+    libtsar_ref.so: get_disp, getview, update_scale_2, update_scale, compute_disp) and its own RANSAC loop
+    (libtsar_ref_host.so) fed with the random stream the command line uses.  Output files bit for bit."""
+    import subprocess
+    import sys
+    import cv2
+    pkg, rb = env
+    from oracle import ref_host_binding as rh
+    from tsar_mvs_b200 import cli, dmb, texture
+    from tsar_mvs_b200.engine import cameras_to_struct
+    assert rh.available()
+    root = str(tmp_path / "ds") + "/"
+    common = ["-mslp_folder", root, "-krt_file", "x", "-no_display", "--cam_scale=1", "--iterations=2", "--blocksize=11",
+              "--cost_comb=best_n", "--n_best=1", f"--seed={SEED}"]
+    r = subprocess.run([sys.executable, os.path.join(pc.ROOT, "tsar_cli.py"), "--synthetic=mid"] + common,
+                       capture_output=True, text=True, cwd=pc.ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    apd = os.path.join(root, "APD", "00000000")
+    # what APD / Fusion would have left in the folder: a depth map, a normal map and weak.png
+    cfg = pkg.scene.CONFIGS["mid"]
+    H, W = cfg["H"], cfg["W"]
+    rng = np.random.RandomState(11)
+    depth_in = dmb.read_dmb(os.path.join(apd, "TSAR_disp.dmb")).astype(np.float32)
+    depth_in[depth_in <= 0] = 1.0
+    normal_in = dmb.read_dmb(os.path.join(apd, "TSAR_normals.dmb")).astype(np.float32)
+    dmb.write_dmb(os.path.join(apd, "depths_geom.dmb"), depth_in)
+    dmb.write_dmb(os.path.join(apd, "normals.dmb"), normal_in)
+    colours = np.array([[255, 255, 255], [0, 255, 0], [0, 0, 255], [0, 0, 0], [255, 0, 0], [254, 255, 255]], np.uint8)   # BGR
+    # 20 % reliable pixels: the facet's region stays below the 50 000 points beyond which the reference cuts the list to a
+    # clock-seeded random subset (main.cpp:1541-1549), which nothing can reproduce
+    weak = colours[rng.choice(len(colours), size=(H, W), p=[0.12, 0.04, 0.04, 0.5, 0.15, 0.15])]
+    cv2.imwrite(os.path.join(apd, "weak.png"), weak)
+    names = sorted(os.listdir(root + "images"))
+    r = subprocess.run([sys.executable, os.path.join(pc.ROOT, "tsar_cli.py")] + names + ["-images_folder", root + "images/", "-import_apd"] + common,
+                       capture_output=True, text=True, cwd=pc.ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "not found" not in r.stderr
+    got_d = dmb.read_dmb(os.path.join(apd, "TSAR_disp.dmb"))
+    got_n = dmb.read_dmb(os.path.join(apd, "TSAR_normals.dmb"))
+
+    # the same flow from the reference's pieces
+    images = [cli._imread_gray(os.path.join(root, "images", n)) for n in names]
+    krt = [cli.read_cam_txt(os.path.join(root, "cams", f"{n[:8]}_cam.txt")) for n in names]
+    cams = pkg.scene.cameras_from_krt([k[0] for k in krt], [k[1] for k in krt], [k[2] for k in krt], krt[0][3], krt[0][4])
+    subset = [s_ for s_ in cli.read_pair_subset(os.path.join(root, "pair.txt"), 0) if s_ < len(names)]
+    f = float(np.float32(cams[0]["f"]))
+    params = pkg.make_params(box=11, iterations=2, n_best=1, cost_comb=1, min_disparity=float(np.float32(f / np.float32(krt[0][4]))),
+                             max_disparity=float(np.float32(f / np.float32(krt[0][3]))))
+    det = texture.detect(images[0].astype(np.uint8))
+    text, size = det["text"], det["size"]
+    weak_regions = [r_ for r_ in range(len(text)) if text[r_] == -1]
+    assert weak_regions, "the detector must flag the textureless facet"
+    canny = texture.expand_labels(det["labels_q"], W, H)
+    ref = rb.RefEngine(pkg._lib.TsarCamera, pkg._lib.TsarParams, variant="asis")
+    ref.create(images, cameras_to_struct(cams), subset, params, f)
+    ref.upload(rb.F_CANNY, canny)
+    ref.upload(rb.F_NORM4, np.concatenate([normal_in, np.zeros((H, W, 1), np.float32)], axis=-1))
+    ref.upload(rb.F_COST, np.ones((H, W), np.float32))
+    ref.upload(rb.F_DEPTH, (np.float32(f) / depth_in).astype(np.float32))
+    ref.get_disp(); ref.getview()
+    reliable = ((weak == [255, 255, 255]).all(-1) | (weak == [0, 255, 0]).all(-1) | (weak == [0, 0, 255]).all(-1)).astype(np.float32)
+    assert 0.18 < reliable.mean() < 0.22
+    assert max(int(((canny == r_) & (reliable == 1)).sum()) for r_ in weak_regions) < 50000
+    ref.upload(rb.F_SCALE, reliable)
+    probe = pkg.DepthmapEngine(0)
+    with np.errstate(over="ignore"):
+        stream = np.concatenate([probe.ransac_rand_stream(SEED, r_) for r_ in weak_regions])
+    probe.close()
+    p0 = np.tile(np.array([0, 0, 1, -1], np.float32), (len(text), 1))
+    planes, used = rh.fit_regions(cams[0], f, ref.download(rb.F_DEPTH), reliable, canny, text, size, stream, p0)
+    assert used == len(stream)
+    ref.set_regions(text, planes)
+    ref.update_scale_2(); ref.update_scale(); ref.compute_disp()
+    want = ref.download(rb.F_NORM4)
+    ref.close()
+    assert pc.frac_bit_exact(got_d, want[..., 3]) == 1.0
+    assert pc.frac_bit_exact(got_n, np.ascontiguousarray(want[..., :3])) == 1.0
+    assert (got_d != depth_in).mean() > 0.01                      # and the completion rewrote the facet
 
 
 def test_plain_c_program_runs_a_depthmap(env, tmp_path):

@@ -215,7 +215,9 @@ int sliccuda(GlobalState &gs_) {
         if ((rc = up(s, TSAR_F_SCALE, gs.lines->scale, n * 4))) return rc;
         for (int iter = 0; iter < 4; iter++)
             if ((rc = tsar_wmf(s.ctx, iter))) return fail(s.ctx, "tsar_wmf", rc);
+        // gipuma_WMF rewrites the reliable flags, the depths and the planes of lines-> in place
         if ((rc = down(s, TSAR_F_SCALE, gs.lines->scale, n * 4))) return rc;
+        if ((rc = down(s, TSAR_F_NORM4, gs.lines->norm4, n * 16))) return rc;
     }
     if ((rc = down(s, TSAR_F_CONFID, gs.lines->confid, n * 4))) return rc;
     return down(s, TSAR_F_DEPTH, gs.lines->depth, n * 4);
