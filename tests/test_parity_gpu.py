@@ -133,20 +133,28 @@ def test_full_sequence_other_windows_and_view_combinations(env, box, n_best, cos
     assert (v_m == v_s).all()
 
 
-def test_fused_equals_unfused(env, small, monkeypatch):
-    """Fusing spatial propagation + refinement of one colour into one kernel changes nothing."""
+@pytest.mark.parametrize("box", [11, 19])
+def test_fused_equals_unfused(env, small, monkeypatch, box):
+    """Fusing spatial propagation + refinement of one colour into one kernel changes nothing.  Runs every instantiation of the
+    checkerboard kernel of a window variant in ONE process (fused, propagation-only, refinement-only; 8-bit and fp32 source
+    textures; pinhole and general intrinsics): with the 19x19 window each of them needs its own opt-in to more than 48 KB
+    of shared memory."""
     pkg, rb = env
-    params, fused, _ = pc.make_engines(pkg, small, iterations=3, variants=())
-    fused.depthmap(SEED)
-    o_f = fused.download(pkg._lib.F_NORM4)
-    monkeypatch.setenv("TSAR_B200_UNFUSED", "1")
-    params, unfused, _ = pc.make_engines(pkg, small, iterations=3, variants=())
-    unfused.depthmap(SEED)
-    o_u = unfused.download(pkg._lib.F_NORM4)
-    n_f, n_u = fused.launch_count(), unfused.launch_count()
-    fused.close(); unfused.close()
-    assert pc.frac_bit_exact(o_f, o_u) == 1.0
-    assert n_u > n_f > 0
+    outs, counts = [], []
+    for envs in ((), (("TSAR_B200_UNFUSED", "1"),), (("TSAR_B200_NO_U8", "1"),), (("TSAR_B200_NO_U8", "1"), ("TSAR_B200_UNFUSED", "1")),
+                 (("TSAR_B200_NO_PINHOLE_FASTPATH", "1"),), (("TSAR_B200_NO_PINHOLE_FASTPATH", "1"), ("TSAR_B200_UNFUSED", "1"))):
+        for k, v in envs:
+            monkeypatch.setenv(k, v)
+        params, eng, _ = pc.make_engines(pkg, small, box=box, iterations=3 if box == 11 else 1, variants=())
+        eng.depthmap(SEED)
+        outs.append(eng.download(pkg._lib.F_NORM4))
+        counts.append(eng.launch_count())
+        eng.close()
+        for k, _ in envs:
+            monkeypatch.delenv(k)
+    for o in outs[1:]:
+        assert pc.frac_bit_exact(outs[0], o) == 1.0
+    assert counts[1] > counts[0] > 0
 
 
 def test_general_intrinsics_instantiation_matches(env, small, monkeypatch):
@@ -706,6 +714,7 @@ FULL_SIZE_CASES = {
     # BASELINE.json configs at their full sizes, 8 iterations, blocksize 11 (the run scripts' settings)
     "C2": "C2",                                                                                     # 3100x2050, V = 10
     "C4": "C4",                                                                                     # 1920x1080, V = 10
+    "C5": "C5",                                                                                     # 6048x4032, V = 20 (about 30 s)
     "C5crop": dict(W=1512, H=1008, n_images=21, V=20, fx=3410.0, radius=6.0, arc_deg=40.0),         # C5's cameras and V = 20 on a crop
 }
 
@@ -721,7 +730,7 @@ def _record(name, obj):
         pass
 
 
-@pytest.mark.parametrize("case", ["C2", "C4", "C5crop"])
+@pytest.mark.parametrize("case", ["C2", "C4", "C5crop", "C5"])
 def test_baseline_size_bit_exact_vs_reference(env, case):
     """The whole per-view sequence (gipuma.cu:1741-1761: init, 8 x (bSP, bPR, rSP, rPR), getlrdiff, getview, compute_disp)
     at BASELINE sizes against the reference's own kernels (race-free twin): depth, normals, confidence, best view and
