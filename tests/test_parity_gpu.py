@@ -1062,6 +1062,19 @@ def test_cli_shipped_flow_from_an_apd_folder(env, tmp_path):
     assert (got_d != depth_in).mean() > 0.01                      # and the completion rewrote the facet
 
 
+def test_every_kernel_and_variant_in_one_process(env):
+    """tools/gpu_sanitize.py drives every kernel of the library -- all window variants (11x11, 19x19, run-time windows, n_best
+    2 / 3, COMB_ALL), fused and unfused launches, odd image sizes, glue, weighted-median stages, region fit (host and device
+    stream), reliable-pixel sources, gSLICr modes, the host entry point -- inside ONE process, which is where per-process state
+    (kernel attributes, persistent scratch, context reuse) can go wrong.  (It is also the script to put under a memory
+    checker where one is available.)"""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(pc.ROOT, "tools", "gpu_sanitize.py")], capture_output=True, text=True, cwd=pc.ROOT)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
+    assert "SANITIZE-SCRIPT-DONE" in r.stdout
+
+
 def test_plain_c_program_runs_a_depthmap(env, tmp_path):
     """examples/c_abi_check.c: a C11 program drives tsar_depthmap_host through the C ABI and recovers a known plane."""
     import subprocess
