@@ -130,6 +130,16 @@ def test_oracle_texture_model_matches_hardware_samples(oracle, tiny):
     assert np.array_equal(got, g["out"][:3000])
 
 
+def test_oracle_texture_model_tie_rule(oracle, tiny):
+    """Hardware samples at coordinates i + 0.5 + k/512: every step of the 8-bit weight grid and every exact tie between two
+    steps (k odd), where the rule -- round half up -- cannot be seen with random coordinates (tools/gpu_tex_ties.py pinned
+    it on a B200: half-up 100 %, half-to-even 53 % on 131 000 ties)."""
+    g = np.load(os.path.join(GOLD, "tiny_tex_ties.npz"))
+    img = tiny["images"][1]
+    got = np.array([oracle.tex(img, x, y) for x, y in g["xy"]], np.float32)
+    assert np.array_equal(got, g["out"])
+
+
 def test_oracle_cost_matches_reference_build(oracle, tiny):
     """pmCostMultiview on 2000 (pixel, plane) pairs.  Not bit-reproducible on a CPU by construction (MUFU.EX2 inside
     CUDA's expf, <= 2 ulp on every bilateral weight).  Tolerance: 5e-5 absolute on a cost in [0, 2] where the window is
