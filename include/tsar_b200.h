@@ -201,7 +201,10 @@ int tsar_download(tsar_ctx *ctx, int field, void *host_dst, size_t bytes);
  * written by the reference).  The output layout is split on the device; host pointers (pinned memory makes the copies
  * asynchronous to other streams); any of them may be NULL. */
 int tsar_download_outputs(tsar_ctx *ctx, float *depth_out, float *normals_out, float *confid_out);
-/* Device pointer of a field (for zero-copy consumers such as a fusion stage on the same GPU). */
+/* Device pointer of a field (for zero-copy consumers such as a fusion stage on the same GPU).  For TSAR_F_NORM4 and
+ * TSAR_F_COST the per-colour double buffers are first merged into the returned array (on the context's stream); the
+ * pointer is valid until the next call that launches propagation or refinement (tsar_launch, tsar_iterate,
+ * tsar_depthmap), after which the live values of one colour sit in the other buffer again. */
 int tsar_device_ptr(tsar_ctx *ctx, int field, void **dev_ptr);
 
 /* ---- whole north-star sequence ------------------------------------------------------------------ */
