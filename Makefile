@@ -4,7 +4,7 @@
 #                      present, oracle/_ref/*.so (the reference's own kernels; test infrastructure)
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Iinclude
+NVFLAGS   := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Iinclude $(EXTRA)
 PKG       := tsar-mvs_b200
 SRC       := $(PKG)/csrc
 BUILD     := build/obj
