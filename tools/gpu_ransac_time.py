@@ -65,6 +65,9 @@ imgs = [im.contiguous() for im in sc2["images"]]
 ref_u8 = imgs[0].cpu().numpy().astype(np.uint8)
 t0 = time.perf_counter()
 det = tx.detect(ref_u8)
+res["c2_detector_host_ms_first_call"] = (time.perf_counter() - t0) * 1e3     # includes importing OpenCV
+t0 = time.perf_counter()
+det = tx.detect(ref_u8)
 res["c2_detector_host_ms"] = (time.perf_counter() - t0) * 1e3
 res["c2_regions"] = int(len(det["text"]))
 res["c2_weak_regions"] = int((det["text"] == -1).sum())
