@@ -903,6 +903,15 @@ def test_cli_all_views_resident_pool(env, tmp_path):
     assert len(pkg.cli._LANE_POOL) == 1
     pkg.cli.release_lanes()
     assert not pkg.cli._LANE_POOL
+    # -resume: only the views whose outputs are missing (or incomplete: a .part file does not count) are computed again
+    os.remove(os.path.join(root, "APD", "00000001", "TSAR_normals.dmb"))
+    os.rename(os.path.join(root, "APD", "00000002", "TSAR_disp.dmb"), os.path.join(root, "APD", "00000002", "TSAR_disp.dmb.part"))
+    res = pkg.cli.run_all_views(dict(opt, resume=True), root, quiet=True)
+    assert res["views"] == 2 and res["skipped"] == n - 2
+    for v in range(n):
+        assert pc.frac_bit_exact(dmb.read_dmb(os.path.join(root, "APD", f"{v:08d}", "TSAR_normals.dmb")), ref_files[v]) == 1.0
+    res = pkg.cli.run_all_views(dict(opt, resume=True), root, quiet=True)
+    assert res["views"] == 0 and res["skipped"] == n
 
 
 def test_labels_quarter_expansion_on_device(env):

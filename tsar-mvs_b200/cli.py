@@ -27,7 +27,9 @@ Extra: `--synthetic=<C1|C2|small|tiny>` first writes a synthetic dataset in the 
 dataset becomes the reference view once.  All images are decoded and uploaded ONCE and stay resident in HBM; each
 reference view binds itself + its pair.txt neighbours from that pool (device-to-device), two contexts on two streams
 pipeline view r+1 behind view r, results are written by a writer pool.  Under torchrun the views are sharded in
-contiguous blocks over the ranks (shard.py), one GPU per rank, no collective.
+contiguous blocks over the ranks (shard.py), one GPU per rank, no collective.  `-resume` skips the views whose three
+output files are already complete (an interrupted run continues where it stopped; files are written under a temporary
+name and renamed, so a partial file never counts).
 """
 import os
 import sys
@@ -42,14 +44,14 @@ NUMERIC = {"blocksize", "iterations", "n_best", "cost_gamma", "depth_min", "dept
            "self_similarity_n", "good_factor", "num_img_processed", "seed", "synthetic", "device", "lanes", "io_threads"}
 PATHS = {"images_folder", "mslp_folder", "krt_file", "output_folder", "p_folder", "camera_folder", "calib_file", "pmvs_folder",
          "bounding_folder", "regions_file", "regions_text", "regions_size"}
-BOOLS = {"color_processing", "view_selection", "import_apd", "no_display", "all_views", "no_weak_texture", "write_ply", "wmf", "no_slic", "no_write"}
+BOOLS = {"color_processing", "view_selection", "import_apd", "no_display", "all_views", "no_weak_texture", "write_ply", "wmf", "no_slic", "no_write", "resume"}
 
 
 def parse_args(argv):
     """getParametersFromCommandLine (main.cpp:708-1009), tolerant in the same places."""
     opt = dict(images=[], blocksize=19, iterations=8, n_best=2, cost_comb=1, cam_scale=1.0, depth_min=-1.0, depth_max=-1.0,
                seed=20240601, device=0, images_folder="", mslp_folder="", output_folder="", synthetic=None,
-               color_processing=False, import_apd=False, all_views=False, no_weak_texture=False, write_ply=False, wmf=False, no_slic=False, no_write=False,
+               color_processing=False, import_apd=False, all_views=False, no_weak_texture=False, write_ply=False, wmf=False, no_slic=False, no_write=False, resume=False,
                regions_file=None, regions_text=None, regions_size=None, lanes=2, io_threads=4)
     i = 0
     while i < len(argv):
@@ -389,6 +391,18 @@ def run_all_views(opt, mslp, quiet=False, persistent=False):
     mine = block_for_rank(len(names), rank, world)      # contiguous blocks: neighbouring views share their source images
     if opt.get("views_per_rank"):                        # warm-up pass of the benchmark: the first few views of each rank
         mine = mine[:int(opt["views_per_rank"])]
+    skipped = []
+    if opt.get("resume"):                                # views whose outputs are complete are not computed again
+        def complete(r):
+            d = os.path.join(mslp, "APD", names[r][:8])
+            return all(os.path.exists(os.path.join(d, f)) for f in ("TSAR_disp.dmb", "TSAR_normals.dmb", "TSAR_confidence.dmb"))
+        skipped = [r for r in mine if complete(r)]
+        mine = [r for r in mine if r not in set(skipped)]
+    if not mine:                                         # nothing (left) to do on this rank
+        if not quiet:
+            print(f"[tsar_cli] rank {rank}/{world}: 0 of {len(names)} reference views to compute ({len(skipped)} already complete)")
+        return dict(rank=rank, world=world, views=0, skipped=len(skipped), images=len(names), seconds=0.0, depthmaps_per_s=0.0, gpu_launches=0,
+                    host_seconds={}, bytes_decoded=0, bytes_written=0, weak_regions=0)
     neigh = {r: [by_id[c] for c in pairs.get(ids[r], []) if c in by_id] for r in mine}
     needed = sorted(set(mine) | {i for r in mine for i in neigh[r]})
     want_colour = not opt["no_slic"]
@@ -474,8 +488,10 @@ def run_all_views(opt, mslp, quiet=False, persistent=False):
         t = time.perf_counter()
         os.makedirs(out_dir, exist_ok=True)
         for name, b in zip(("TSAR_disp.dmb", "TSAR_normals.dmb", "TSAR_confidence.dmb"), bufs):
-            with open(os.path.join(out_dir, name), "wb", buffering=0) as f:
+            tmp = os.path.join(out_dir, name + ".part")
+            with open(tmp, "wb", buffering=0) as f:
                 f.write(memoryview(b.numpy()))
+            os.replace(tmp, os.path.join(out_dir, name))     # a file under its final name is always complete (-resume)
         free.put(bufs)
         add("write_s", time.perf_counter() - t)
 
@@ -541,7 +557,7 @@ def run_all_views(opt, mslp, quiet=False, persistent=False):
     io_pool.shutdown()
     stats["until_first_view_s"] = marks["first_view_start"] or 0.0      # timeline of the pass (not summed over threads)
     stats["after_last_view_s"] = dt - (marks["last_view_done"] or dt)
-    res = dict(rank=rank, world=world, views=len(done), images=len(names), W=W, H=H, seconds=dt, depthmaps_per_s=len(done) / dt,
+    res = dict(rank=rank, world=world, views=len(done), skipped=len(skipped), images=len(names), W=W, H=H, seconds=dt, depthmaps_per_s=len(done) / dt,
                lanes=n_lanes, io_threads=int(opt["io_threads"]), gpu_launches=int(launches),
                host_seconds={k: round(v, 3) for k, v in stats.items()},
                bytes_decoded=int(sum(os.path.getsize(os.path.join(folder, names[i])) for i in needed)),
