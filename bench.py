@@ -35,6 +35,25 @@ FLOPS_PER_EVAL = 1590.0      # 40*S + 150 at S = 36 (as w
 FLOPS_PER_EVAL_19 = 4150.0   # S = 100
 FP32_NOMINAL_TFLOPS = 74.5   # 148 SM x 128 lanes x 2 x 1.965 GHz
 
+# stdout carries the ONE JSON line and nothing else: libraries write there too (NCCL prints its version line on stdout, the
+# reference's kernels printf debug lines, gipuma.cu:1043-1045), so file descriptor 1 is pointed at stderr for the whole run
+# and the line goes to a duplicate of the real stdout.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -119,6 +138,7 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not precede the JSON line on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
@@ -381,7 +401,7 @@ def run_ours(args):
             out["cpu_baseline"] = cpu_baseline(pkg, cfg, n_evals)
         except Exception as e:  # the baseline must not take the bench down
             out["cpu_baseline"] = {"error": repr(e)}
-    print(json.dumps(out), flush=True)
+    emit(out)
     shutdown(world)
 
 
@@ -458,7 +478,7 @@ def run_product(args):
                         "per_pass_seconds": secs, "dataset_generation_s": t_gen, "host_cores": os.cpu_count()},
             "clocks": clk.summary(),
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     pkg.cli.release_lanes()
     barrier(world)
     if rank == 0:
@@ -471,15 +491,6 @@ def run_reference(args):
     per reference view on one GPU (scripts/pipes.sh:30-49), so under torchrun EVERY rank runs its own stream of reference
     views on its own GPU, exactly like our arm; the time is the max over ranks and rank 0 prints the line.  Nothing of
     libtsar_b200.so is loaded here: struct layouts and the closed-form evaluation count are pure Python."""
-    # the reference kernels printf debug lines ("after prop : ...", gipuma.cu:1043-1045): keep stdout for the JSON line
-    sys.stdout.flush()
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
-
-    def emit(obj):
-        sys.stdout.flush()
-        os.dup2(real_stdout, 1)
-        print(json.dumps(obj), flush=True)
     import torch
     import __graft_entry__ as g
     pkg = g.load_package()
@@ -552,13 +563,14 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
+    capture_stdout()
     driver = a.config in PRODUCT_CONFIGS and a.mode != "engine"
     if a.mode == "driver" and a.config not in PRODUCT_CONFIGS:
         sys.exit(f"--mode driver needs one of {sorted(PRODUCT_CONFIGS)}")
     if a.impl == "reference" and driver:
         if int(os.environ.get("RANK", "0")) == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "the reference has no multi-view driver (one process per view, scripts/pipes.sh); "
-                                                                   "its per-view rate is measured by --config C2 --impl reference"}), flush=True)
+            emit({"impl": "reference", "unavailable": "the reference has no multi-view driver (one process per view, scripts/pipes.sh); "
+                                                      "its per-view rate is measured by --config C2 --impl reference"})
     elif a.impl == "reference":
         run_reference(a)
     elif driver:
