@@ -1,0 +1,62 @@
+#!/usr/bin/env python3
+"""One-off differential stress of the whole per-view sequence against the race-free reference build: many random
+configurations (odd sizes, 1..12 source views, windows 5..25, n_best 1..3, both view combinations, 1..3 iterations,
+random depth ranges and seeds; a third of them with images that are NOT 8-bit valued, i.e. fp32 textures, and a third
+with skewed / non-square intrinsics, i.e. the general homography instantiation).  The GPU suite runs 8 such trials
+(test_randomized_configurations_bit_exact); this runs N (default 120) and records every configuration.
+
+    python tools/gpu_parity_sweep.py [N]   ->  gpurun_out/r02_parity_sweep.json
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tests import parity_common as pc  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 120
+pkg = pc.load_pkg()
+L = pkg._lib
+rb = pc.ref_binding()
+rng = np.random.RandomState(424242)
+rows, bad = [], 0
+for trial in range(N):
+    W, H = int(rng.randint(36, 360)), int(rng.randint(34, 260))
+    V = int(rng.randint(1, 13))
+    box = int(rng.choice([5, 7, 9, 11, 11, 11, 12, 13, 15, 19, 19, 25]))
+    n_best = int(rng.randint(1, min(V, 3) + 1))
+    cost_comb = int(rng.choice([0, 1]))
+    cfg = dict(W=W, H=H, n_images=V + 1, V=V, fx=float(rng.uniform(120, 500)), radius=float(rng.uniform(0.8, 3.0)),
+               arc_deg=float(rng.uniform(6, 30)))
+    scene = pkg.scene.make_scene(cfg, seed=int(rng.randint(1, 100000)))
+    kind = trial % 3
+    if kind == 1:      # images with fractional grey values: the 8-bit texture copies cannot be used
+        scene["images"] = [np.ascontiguousarray(im + rng.uniform(0, 0.9, im.shape).astype(np.float32)) for im in scene["images"]]
+    if kind == 2:      # skew and different focal lengths: not the zero-skew pinhole pattern
+        for c in scene["cams"]:
+            K = np.array(c["K"], float).reshape(3, 3).copy()
+            K[0, 1] = rng.uniform(-3, 3)
+            K[1, 1] *= rng.uniform(0.9, 1.1)
+            c["K"] = K
+            c["K_inv"] = np.linalg.inv(K)
+    iters = int(rng.randint(1, 4))
+    params, mine, refs = pc.make_engines(pkg, scene, iterations=iters, box=box, n_best=n_best, cost_comb=cost_comb, variants=("snapshot",))
+    ref = refs["snapshot"]
+    seed = int(rng.randint(1, 2 ** 31))
+    mine.depthmap(seed); ref.depthmap(seed, iters=iters)
+    row = dict(trial=trial, W=W, H=H, V=V, box=box, n_best=n_best, cost_comb=cost_comb, iters=iters, kind=("u8", "fp32 texels", "general intrinsics")[kind],
+               output=pc.frac_bit_exact(mine.download(L.F_NORM4), ref.download(rb.F_NORM4)),
+               confidence=pc.frac_bit_exact(mine.download(L.F_CONFID), ref.download(rb.F_CONFID)),
+               best_view=float((mine.download(L.F_BEVIEW) == ref.download(rb.F_BEVIEW)).mean()))
+    mine.close(); ref.close()
+    ok = row["output"] == 1.0 and row["confidence"] == 1.0 and row["best_view"] == 1.0
+    bad += 0 if ok else 1
+    rows.append(row)
+    print(("ok  " if ok else "FAIL"), json.dumps(row), flush=True)
+res = dict(trials=N, bit_exact_trials=N - bad, failing=[r for r in rows if not (r["output"] == 1.0 and r["confidence"] == 1.0 and r["best_view"] == 1.0)], rows=rows)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "r02_parity_sweep.json"), "w"), indent=1)
+print(f"{N - bad} of {N} configurations bit-exact")
+sys.exit(1 if bad else 0)
