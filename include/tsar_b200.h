@@ -254,6 +254,11 @@ int tsar_dbg_tex_formats(tsar_ctx *ctx, int image, int n, const float *xy, float
  * per source view), bitwise duplicates of the pixel's own plane, duplicates of an earlier candidate of the same pixel,
  * distinct candidates; warp-wide evaluation rounds as written / with per-lane lists of distinct candidates / perfectly
  * packed; warps; the same three figures without the own-plane rule; then pixels by number of distinct candidates 0..8. */
+/* Debug: superpixel records of the last tsar_slic call, 8 words each in the layout of gSLICr::objects::spixel_info
+ * (gSLICr_spixel_info.h:10-16: centre x, y; colour x, y, z, w; int id; int no_pixels). */
+int tsar_dbg_slic_centres(tsar_ctx *ctx, float *out, int max_records, int *n_records);
+/* Debug: the CIELAB image (4 floats per pixel) tsar_slic computed from its last input (rgb2CIELab, gSLICr_seg_engine_shared.h:30-59). */
+int tsar_dbg_slic_lab(tsar_ctx *ctx, float *out, size_t n_pixels);
 int tsar_dbg_candidate_stats(tsar_ctx *ctx, int colour, unsigned long long *out22);
 /* Test-only: tsar_eval_planes normally rounds H*(x,y,1) as the reference's real kernels do
  * (fma(m0,x, m1*y) + m2).  The oracle's stand-alone wrapper kernel around pmCostMultiview_cu is compiled

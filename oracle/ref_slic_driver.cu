@@ -38,6 +38,32 @@ void seg_engine::Perform_Segmentation(UChar4Image *in_img, GlobalState *) {
     cudaDeviceSynchronize();
 }
 
+// superpixel records (centre x, y, colour x, y, z, w, id, no_pixels = 8 words each) and the Lab image of the last ref_slic
+// call, for stage-by-stage comparisons
+namespace {
+struct PeekEngine : public seg_engine_GPU {
+    PeekEngine(const settings &s) : seg_engine_GPU(s) {}
+    SpixelMap *map() { return spixel_map; }
+    Float4Image *lab() { return cvt_img; }
+};
+float *g_centres = nullptr;
+int g_n_centres = 0;
+float *g_lab = nullptr;
+size_t g_n_lab = 0;
+}  // namespace
+
+extern "C" long long ref_slic_last_lab(float *out, long long max_pixels) {   // Lab image (4 floats per pixel) of the last call
+    const size_t n = g_n_lab < (size_t)max_pixels ? g_n_lab : (size_t)max_pixels;
+    if (out && g_lab) memcpy(out, g_lab, n * 16);
+    return (long long)g_n_lab;
+}
+
+extern "C" int ref_slic_last_centres(float *out, int max_records) {
+    const int n = g_n_centres < max_records ? g_n_centres : max_records;
+    if (out && g_centres) memcpy(out, g_centres, (size_t)n * 32);
+    return g_n_centres;
+}
+
 extern "C" int ref_slic(const unsigned char *bgrx, int w, int h, int spixel_size, int no_iters, float coh_weight,
                         int enforce, int *labels_out, float *ms_out) {
     settings s;
@@ -50,7 +76,7 @@ extern "C" int ref_slic(const unsigned char *bgrx, int w, int h, int spixel_size
     s.color_space = CIELAB;      // :613
     s.seg_method = GIVEN_SIZE;   // :614
     s.do_enforce_connectivity = enforce != 0;  // :615
-    seg_engine_GPU *eng = new seg_engine_GPU(s);
+    PeekEngine *eng = new PeekEngine(s);
     UChar4Image *in_img = new UChar4Image(s.img_size, true, true);
     memcpy(in_img->GetData(MEMORYDEVICE_CPU), bgrx, (size_t)w * h * 4);
     cudaEvent_t e0, e1;
@@ -65,6 +91,20 @@ extern "C" int ref_slic(const unsigned char *bgrx, int w, int h, int spixel_size
     if (ms_out) *ms_out = ms;
     const IntImage *res = eng->Get_Seg_Mask();
     memcpy(labels_out, res->GetData(MEMORYDEVICE_CPU), (size_t)w * h * sizeof(int));
+    {
+        SpixelMap *m = eng->map();
+        m->UpdateHostFromDevice();
+        g_n_centres = m->noDims.x * m->noDims.y;
+        delete[] g_centres;
+        g_centres = new float[(size_t)g_n_centres * 8];
+        memcpy(g_centres, m->GetData(MEMORYDEVICE_CPU), (size_t)g_n_centres * 32);
+        Float4Image *l = eng->lab();
+        l->UpdateHostFromDevice();
+        g_n_lab = (size_t)w * h;
+        delete[] g_lab;
+        g_lab = new float[g_n_lab * 4];
+        memcpy(g_lab, l->GetData(MEMORYDEVICE_CPU), g_n_lab * 16);
+    }
     cudaError_t err = cudaGetLastError();
     delete in_img;
     delete eng;

@@ -406,6 +406,17 @@ def test_slic_labels_bit_exact(env, cfg, size, enforce):
     assert (full >= 0).all() and full.max() < (bgrx.shape[0] // size) * (bgrx.shape[1] // size)
 
 
+def test_slic_stages_bit_exact_and_exact_ties(env):
+    """Beyond the final labels (tools/gpu_slic_stages.py): rgb2CIELab over its whole input domain -- every 24-bit colour
+    once -- and the superpixel records (centre, colour, count) after every iteration, bit for bit against the reference
+    engine, on a piecewise-constant image: there the distances of a pixel to two centres tie exactly and the last ulp of
+    the compiled contraction decides the label (found in round 2: 0.1 % of the labels of one such image differed)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(pc.ROOT, "tools", "gpu_slic_stages.py")], capture_output=True, text=True, cwd=pc.ROOT)
+    assert r.returncode == 0 and "ALL EXACT" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
 def test_gslicr_core_engine_drop_in(env, tmp_path):
     """gSLICr::engines::core_engine exported by libtsar_b200.so under the reference's mangled names, driven by a harness
     compiled against the REFERENCE's own gSLICr / ORUtils headers that plays gslic() (main.cpp:598-660): labels equal the

@@ -1090,6 +1090,38 @@ int tsar_slic(tsar_ctx *ctx, const unsigned char *bgrx, const tsar_slic_settings
     return TSAR_OK;
 }
 
+// debug: the superpixel records of the last tsar_slic call (8 words each: centre x, y, colour x, y, z, w, id, no_pixels,
+// the layout of gSLICr::objects::spixel_info), for stage-by-stage comparison with the reference engine
+int tsar_dbg_slic_centres(tsar_ctx *ctx, float *out, int max_records, int *n_records) {
+    if (!ctx || !n_records) return TSAR_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->slic.last_nsp;
+    *n_records = n;
+    const int m = n < max_records ? n : max_records;
+    if (out && m > 0) {
+        std::vector<SpixelInfo> host(m);   // the device record is 48 bytes (float4 alignment); the reference's is 32
+        CK(cudaMemcpyAsync(host.data(), ctx->slic.d_sp, (size_t)m * sizeof(SpixelInfo), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < m; i++) {
+            float *o = out + 8 * (size_t)i;
+            o[0] = host[i].cx; o[1] = host[i].cy;
+            o[2] = host[i].color.x; o[3] = host[i].color.y; o[4] = host[i].color.z; o[5] = host[i].color.w;
+            memcpy(o + 6, &host[i].id, 4); memcpy(o + 7, &host[i].no_pixels, 4);
+        }
+    }
+    return TSAR_OK;
+}
+
+// debug: the CIELAB image of the last tsar_slic call (4 floats per pixel)
+int tsar_dbg_slic_lab(tsar_ctx *ctx, float *out, size_t n_pixels) {
+    if (!ctx || !out) return TSAR_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n_pixels > (size_t)ctx->slic.cap_px || !ctx->slic.d_lab) FAIL(TSAR_ERR_ARG, "no Lab image of that size (run tsar_slic first)");
+    CK(cudaMemcpyAsync(out, ctx->slic.d_lab, n_pixels * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSAR_OK;
+}
+
 int tsar_launch_count(tsar_ctx *ctx, long long *count, int reset) {
     if (!ctx || !count) return TSAR_ERR_ARG;
     *count = ctx->launches;

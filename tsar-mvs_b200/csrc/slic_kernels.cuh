@@ -21,7 +21,7 @@
 
 namespace tsar {
 
-struct SpixelInfo {  // == gSLICr::objects::spixel_info (gSLICr_spixel_info.h:10-16), 32 bytes
+struct SpixelInfo {  // the fields of gSLICr::objects::spixel_info (gSLICr_spixel_info.h:10-16); 48 bytes here (float4 alignment)
     float cx, cy;
     float4 color;
     int id;
@@ -30,6 +30,7 @@ struct SpixelInfo {  // == gSLICr::objects::spixel_info (gSLICr_spixel_info.h:10
 
 struct SlicState {
     int cap_px = 0, cap_sp = 0;
+    int last_nsp = 0;       // superpixels of the last run (debug read-back)
     uchar4 *d_in = nullptr;
     float4 *d_lab = nullptr;
     int *d_idx = nullptr, *d_tmp = nullptr;
@@ -92,9 +93,13 @@ __global__ void slic_assign_kernel(const float4 *__restrict__ lab, const SpixelI
             if (xx >= 0 && yy >= 0 && xx < mw && yy < mh) {
                 const SpixelInfo c = sp[yy * mw + xx];
                 const float d0 = fsub(pix.x, c.color.x), d1 = fsub(pix.y, c.color.y), d2 = fsub(pix.z, c.color.z);
-                const float dcolor = __fsqrt_rn(ffma(d2, d2, ffma(d1, d1, fmul(d0, d0))));
+                // contraction as compiled in all nine unrolled candidates of the reference build (SASS of
+                // Find_Center_Association_device): the MIDDLE square is rounded first and the others fused on top, like every
+                // 3-term sum of products there; of two squares the second is rounded first.  A last-ulp matter that decides
+                // exact ties only (piecewise-constant images) -- found by tools/gpu_slic_sweep.py in round 2.
+                const float dcolor = __fsqrt_rn(ffma(d2, d2, ffma(d0, d0, fmul(d1, d1))));
                 const float ex = fsub((float)x, c.cx), ey = fsub((float)y, c.cy);
-                const float dxy = __fsqrt_rn(ffma(ey, ey, fmul(ex, ex)));
+                const float dxy = __fsqrt_rn(ffma(ex, ex, fmul(ey, ey)));
                 const float t = fmul(fmul(dxy, norm_xy), weight);
                 const float cd = __fsqrt_rn(ffma(dcolor, dcolor, fmul(t, t)));
                 if (cd < dist) { dist = cd; minidx = c.id; }
@@ -215,12 +220,14 @@ static inline const char *slic_run(SlicState &st, const unsigned char *bgrx, con
     const int mw = w / size, mh = h / size;  // (int)ceil(int/int): the division truncates first (GPU.cu:74-75)
     if (mw < 1 || mh < 1) return "tsar_slic: image smaller than one superpixel";
     const int npx = w * h, nsp = mw * mh;
+    st.last_nsp = nsp;
     if (npx > st.cap_px || nsp > st.cap_sp) {
         slic_free(st);
         if (cudaMalloc(&st.d_in, (size_t)npx * 4) || cudaMalloc(&st.d_lab, (size_t)npx * 16) || cudaMalloc(&st.d_idx, (size_t)npx * 4) ||
             cudaMalloc(&st.d_tmp, (size_t)npx * 4) || cudaMalloc(&st.d_sp, (size_t)nsp * sizeof(SpixelInfo)))
             return "tsar_slic: cudaMalloc failed";
         st.cap_px = npx; st.cap_sp = nsp;
+        st.last_nsp = nsp;
     }
     const int nblocks = (int)ceilf((float)(size * size * 9) / 256.0f);  // no_grid_per_center (GPU.cu:80-82)
     const int nbpl = size * 3 / 16;                                     // no_blocks_per_line (GPU.cu:160)
