@@ -51,6 +51,17 @@ if need "$OUT/libtsar_ref_snap.so" "$HERE/ref_driver.cu" "$REF/gipuma.cu" "$HERE
       -e '1470,1485s/gs\.lines->scale\[pindex\]/gs.lines->ransa[pindex]/g' \
       "$REF/gipuma.cu" > "$TMP/gipuma_snapshot.cu"
   $NVCC $COMMON -DORACLE_SNAPSHOT -I"$TMP" -I"$REF" "$HERE/ref_driver.cu" -o "$OUT/libtsar_ref_snap.so"
+  # 2b. the same twin with ONE more change: `float4 norm_mid;` of gipuma_WMF / gipuma_WMF_Final (gipuma.cu:1423, 1625) is
+  # zero-initialised.  As written the reference reads that variable uninitialised whenever a weighted median is never
+  # reached (tiny neighbour lists), so it is undefined there; with the initialisation it is defined everywhere, which lets
+  # the weighted-median kernels be compared at 100 % instead of "up to the undefined pixels".
+  sed -n '1423p' "$REF/gipuma.cu" | grep -q 'float4 norm_mid;'
+  sed -n '1625p' "$REF/gipuma.cu" | grep -q 'float4 norm_mid;'
+  sed -e '1423s/float4 norm_mid;/float4 norm_mid = make_float4(0.f, 0.f, 0.f, 0.f);/' \
+      -e '1625s/float4 norm_mid;/float4 norm_mid = make_float4(0.f, 0.f, 0.f, 0.f);/' \
+      "$TMP/gipuma_snapshot.cu" > "$TMP/gipuma_snapshot_init.cu"
+  mv "$TMP/gipuma_snapshot_init.cu" "$TMP/gipuma_snapshot.cu"
+  $NVCC $COMMON -DORACLE_SNAPSHOT -DORACLE_WMF_INIT -I"$TMP" -I"$REF" "$HERE/ref_driver.cu" -o "$OUT/libtsar_ref_snapinit.so"
   rm -rf "$TMP"; trap - EXIT
 fi
 

@@ -17,8 +17,13 @@ F_NORM4, F_COST, F_DEPTH, F_FAKEDEPTH, F_SCALE, F_CANNY, F_RATIO, F_BEVIEW, F_LR
 _DT = {F_NORM4: (np.float32, 4), F_BEVIEW: (np.int32, 1), F_REGION_NORM4: (np.float32, 4)}
 
 
+# 'asis': gipuma.cu unmodified; 'snapshot': the race-free twin (2-line store redirection); 'snapshot_init': the twin with
+# gipuma_WMF's / gipuma_WMF_Final's norm_mid zero-initialised (defined where the reference reads it uninitialised)
+_LIB_OF = {"asis": "libtsar_ref.so", "snapshot": "libtsar_ref_snap.so", "snapshot_init": "libtsar_ref_snapinit.so"}
+
+
 def available(variant="asis"):
-    return os.path.exists(os.path.join(REF_DIR, "libtsar_ref.so" if variant == "asis" else "libtsar_ref_snap.so"))
+    return os.path.exists(os.path.join(REF_DIR, _LIB_OF[variant]))
 
 
 class RefEngine:
@@ -26,7 +31,7 @@ class RefEngine:
     'snapshot' (2-line build-time patch: deterministic pre-launch-snapshot semantics)."""
 
     def __init__(self, camera_struct_type, params_struct_type, variant="asis"):
-        name = "libtsar_ref.so" if variant == "asis" else "libtsar_ref_snap.so"
+        name = _LIB_OF[variant]
         self.lib = C.CDLL(os.path.join(REF_DIR, name))
         self.variant = variant
         self.Cam, self.Par = camera_struct_type, params_struct_type

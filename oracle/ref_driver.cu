@@ -112,7 +112,9 @@ static void fill_cam(Camera_cu &c, const tsar_camera &s) {
 extern "C" {
 
 const char *ref_variant(void) {
-#ifdef ORACLE_SNAPSHOT
+#if defined(ORACLE_SNAPSHOT) && defined(ORACLE_WMF_INIT)
+    return "snapshot_init";   // snapshot twin + zero-initialised norm_mid in gipuma_WMF / gipuma_WMF_Final (build_ref.sh 2b)
+#elif defined(ORACLE_SNAPSHOT)
     return "snapshot";
 #else
     return "asis";

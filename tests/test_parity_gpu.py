@@ -564,15 +564,21 @@ def test_reference_entry_points_drop_in(env, small):
     eng.close()
 
 
-def test_wmf_and_wmf_final_bit_exact(env, small):
+@pytest.mark.parametrize("variant", ["snapshot_init", "snapshot"])
+def test_wmf_and_wmf_final_bit_exact(env, small, variant):
     """gipuma_WMF x4 and gipuma_WMF_Final x6 (gipuma.cu:1500-1698, 1295-1497; launch sites 1809-1812, 1844-1847)
     against the race-free reference build: scale after every consistency level, then planes/disparities/flags after
-    every fill level.  Includes the reference's bubble-sort off-by-one (dummy element, largest element dropped)."""
+    every fill level.  Includes the reference's bubble-sort off-by-one (dummy element, largest element dropped).
+    When a weighted median is never reached (tiny neighbour lists) the reference reads its `float4 norm_mid` uninitialised
+    (gipuma.cu:1423, 1625), i.e. is undefined there.  Variant 'snapshot_init' is the twin with that ONE variable
+    zero-initialised at build time (oracle/build_ref.sh 2b): against it every pixel of every level must agree, 100 %.
+    Against the twin as written the same comparison may differ on the undefined pixels only (bounded, < 5e-4)."""
     pkg, rb = env
     L = pkg._lib
     scene = small
-    params, mine, refs = pc.make_engines(pkg, scene, iterations=3, variants=("snapshot",))
-    ref = refs["snapshot"]
+    params, mine, refs = pc.make_engines(pkg, scene, iterations=3, variants=(variant,))
+    ref = refs[variant]
+    bound = 0.0 if variant == "snapshot_init" else 5e-4
     ref.init_planes(SEED); ref.iterate(3, SEED); ref.lrdiff(); ref.getview()
     n0, c0, d0 = ref.download(rb.F_NORM4), ref.download(rb.F_COST), ref.download(rb.F_DEPTH)
     reliable = (c0 < 0.25).astype(np.float32)          # stands in for APD's weak.png (main.cpp:1499-1514)
@@ -590,7 +596,7 @@ def test_wmf_and_wmf_final_bit_exact(env, small):
         worst = max(worst, float((s_m != s_r).mean()))
         changed = max(changed, float((s_r != reliable).mean()))
     print(f"\n[wmf] worst per-level label mismatch {worst:.5%}")
-    assert worst < 5e-4
+    assert worst <= bound
     assert changed > 0.01                                # the filter really re-classified pixels
     for e in (mine, ref):
         e.set_regions(scene["region_text"], scene["region_norm4"])
@@ -604,28 +610,35 @@ def test_wmf_and_wmf_final_bit_exact(env, small):
             a, b = mine.download(fm), ref.download(fr)
             miss = 1 - pc.frac_bit_exact(a, b)
             worst = max(worst, miss)
-            assert miss < 5e-4, f"WMF_Final level {it} field {fm}: {miss:.4%} differ"
+            assert miss <= bound, f"WMF_Final level {it} field {fm}: {miss:.4%} differ"
     print(f"[wmf_final] worst per-level mismatch {worst:.5%}")
     assert (ref.download(rb.F_SCALE) != before).mean() > 0.001   # pixels were filled
     mine.close(); ref.close()
 
 
-def test_wmf_cooperative_equals_per_thread(env, monkeypatch):
+@pytest.mark.parametrize("density", [0.9, 0.03])
+def test_wmf_cooperative_equals_per_thread(env, monkeypatch, density):
     """The warp-cooperative gipuma_WMF (bitonic sort of (key, slot) composites, sequential sums by one lane) and the
     per-thread implementation (merge sort in local memory) give identical flags on every level, on an image with
-    borders, unreliable areas and ties (propagated planes are exact copies)."""
+    borders, unreliable areas and ties (propagated planes are exact copies) -- and on a SPARSE reliable mask (3 %), where
+    most pixels have one or two reliable neighbours and the bubble sort's dummy element is the one that reaches half the
+    weight: the reference then takes pixel (0, 0) as the median's pixel (found by tools/gpu_wmf_sweep.py in round 2: the
+    cooperative kernel got that case wrong, up to 12 % of the flags of such a level)."""
     pkg, rb = env
     L = pkg._lib
     cfg = dict(W=333, H=201, n_images=3, V=2, fx=400.0, radius=2.0, arc_deg=12.0)
     scene = pkg.scene.make_scene(cfg)
-    params, mine, _ = pc.make_engines(pkg, scene, iterations=2, variants=())
+    params, mine, refs = pc.make_engines(pkg, scene, iterations=2, variants=("snapshot_init",))
+    ref = refs["snapshot_init"]
     mine.depthmap(SEED)
     mine.init_planes(SEED); mine.iterate(2, SEED); mine.lrdiff(); mine.getview()
     cost = mine.download(L.F_COST)
     rng = np.random.RandomState(4)
-    reliable = ((cost < 0.3) & (rng.rand(*cost.shape) < 0.9)).astype(np.float32)
+    reliable = ((cost < (0.3 if density > 0.5 else 3.0)) & (rng.rand(*cost.shape) < density)).astype(np.float32)
     reliable[:, :40] = 0                                   # a band with (almost) no reliable neighbours
     reliable[60:64, 100:104] = 1
+    # the same state on the reference twin (zero-initialised norm_mid: defined everywhere)
+    ref.upload(rb.F_NORM4, mine.download(L.F_NORM4)); ref.upload(rb.F_COST, cost); ref.upload(rb.F_DEPTH, mine.download(L.F_DEPTH))
     outs = {}
     for mode in ("0", "1"):
         monkeypatch.setenv("TSAR_B200_WMF_PER_THREAD", mode)
@@ -636,10 +649,17 @@ def test_wmf_cooperative_equals_per_thread(env, monkeypatch):
             levels.append(mine.download(L.F_SCALE).copy())
         outs[mode] = levels
     monkeypatch.delenv("TSAR_B200_WMF_PER_THREAD")
-    mine.close()
+    ref.upload(rb.F_SCALE, reliable)
+    ref_levels = []
+    for it in range(4):
+        ref.wmf(it)
+        ref_levels.append(ref.download(rb.F_SCALE).copy())
+    mine.close(); ref.close()
     for it in range(4):
         assert np.array_equal(outs["0"][it], outs["1"][it]), (it, float((outs["0"][it] != outs["1"][it]).mean()))
-    assert 0.05 < outs["0"][3].mean() < 0.999
+        assert np.array_equal(outs["0"][it], ref_levels[it]), (it, float((outs["0"][it] != ref_levels[it]).mean()))
+    if density > 0.5:
+        assert 0.05 < outs["0"][3].mean() < 0.999
 
 
 def test_region_plane_fit_matches_reference_code(env, small):

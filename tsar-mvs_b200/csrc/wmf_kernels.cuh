@@ -368,9 +368,13 @@ __global__ void __launch_bounds__(256, 5) wmf_coop_kernel(const __grid_constant_
         if (hy >= 0) norm_mid.y = sm.y[l][hy];
         if (hz >= 0) norm_mid.z = sm.z[l][hz];
         if (hd >= 0) {
+            // weimid.  The dummy element can be the one that reaches half: with a single reliable neighbour of positive
+            // depth the sorted list is (dummy, neighbour), only position 0 counts, wSum = 0.  Its index is 0 in the
+            // reference's zero-initialised list, so the reference then takes pixel (0, 0) and ITS depth.
+            const bool dummy = hd == kCoopDummy;
             const int ii = hd / 11, jj = hd - ii * 11;
-            const int mx = px - radius + ii * gap, my = y - radius + jj * gap;  // weimid
-            const float disp_mid = fdiv(fmul(g.f_params, g.baseline), sm.d[l][hd]);
+            const int mx = dummy ? 0 : px - radius + ii * gap, my = dummy ? 0 : y - radius + jj * gap;
+            const float disp_mid = fdiv(fmul(g.f_params, g.baseline), dummy ? depth[0] : sm.d[l][hd]);
             const float len = __fsqrt_rn(dot3(norm_mid.x, norm_mid.x, norm_mid.y, norm_mid.y, norm_mid.z, norm_mid.z));
             norm_mid.x = fdiv(norm_mid.x, len); norm_mid.y = fdiv(norm_mid.y, len); norm_mid.z = fdiv(norm_mid.z, len);
             norm_mid.w = g_plane_d(g, norm_mid.x, norm_mid.y, norm_mid.z, mx, my, disp_mid);
