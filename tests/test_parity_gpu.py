@@ -1115,6 +1115,20 @@ def test_every_kernel_and_variant_in_one_process(env):
     assert "SANITIZE-SCRIPT-DONE" in r.stdout
 
 
+@pytest.mark.parametrize("script,args", [("gpu_cost_sweep.py", ["4", "30000"]), ("gpu_glue_sweep.py", ["8"]), ("gpu_slic_sweep.py", ["45"]),
+                                         ("gpu_wmf_sweep.py", ["8"]), ("gpu_ransac_sweep.py", ["8"])])
+def test_differential_sweeps(env, script, args):
+    """Short runs of the differential sweeps (tools/README.md): every component against the reference's own code on random and
+    adversarial inputs -- hostile planes for the cost (exact-division path, NaN / inf), NaN / inf state for the per-pixel
+    kernels, piecewise-constant images for gSLICr (exact ties), sparse reliable masks for the weighted medians (dummy-element
+    medians), degenerate and collinear regions for the RANSAC fit (NaN planes).  Each script exits non-zero on the first
+    configuration that is not bit-exact; the long runs are recorded under profiles/r02_*_sweep.json."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(pc.ROOT, "tools", script)] + args, capture_output=True, text=True, cwd=pc.ROOT)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
+
+
 def test_plain_c_program_runs_a_depthmap(env, tmp_path):
     """examples/c_abi_check.c: a C11 program drives tsar_depthmap_host through the C ABI and recovers a known plane."""
     import subprocess
