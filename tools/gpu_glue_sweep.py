@@ -21,7 +21,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 pkg = pc.load_pkg()
 L = pkg._lib
 rb = pc.ref_binding()
-rng = np.random.RandomState(99)
+rng = np.random.RandomState(int(os.environ.get("TSAR_SWEEP_SEED", "99")))   # TSAR_SWEEP_SEED: another campaign
 FIELDS = (("norm4", L.F_NORM4, rb.F_NORM4), ("cost", L.F_COST, rb.F_COST), ("depth", L.F_DEPTH, rb.F_DEPTH),
           ("fakedepth", L.F_FAKEDEPTH, rb.F_FAKEDEPTH), ("scale", L.F_SCALE, rb.F_SCALE), ("lrdiff", L.F_LRDIFF, rb.F_LRDIFF),
           ("confid", L.F_CONFID, rb.F_CONFID))

@@ -21,7 +21,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 pkg = pc.load_pkg()
 L = pkg._lib
 rb = pc.ref_binding()
-rng = np.random.RandomState(424242)
+rng = np.random.RandomState(int(os.environ.get("TSAR_SWEEP_SEED", "424242")))   # TSAR_SWEEP_SEED: another campaign
 rows, bad = [], 0
 for trial in range(N):
     W, H = int(rng.randint(36, 360)), int(rng.randint(34, 260))

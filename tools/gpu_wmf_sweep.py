@@ -21,7 +21,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 pkg = pc.load_pkg()
 L = pkg._lib
 rb = pc.ref_binding()
-rng = np.random.RandomState(31337)
+rng = np.random.RandomState(int(os.environ.get("TSAR_SWEEP_SEED", "31337")))   # TSAR_SWEEP_SEED: another campaign
 rows, bad = [], 0
 for trial in range(N):
     W, H = int(rng.randint(60, 420)), int(rng.randint(50, 300))
